@@ -1,0 +1,395 @@
+// Operand preparation kernels (HBM-bound, CUDA cores):
+//   - normalize_rows : L variant -- layer selection + L2 normalise + mask + fp16
+//   - cast_rows_bf16 : LE/LEF    -- layer selection + bf16 cast, layer-major rows
+//   - temporal       : LEF       -- Conv1d(k3)+BN(folded)+MaxPool1d(3,2,1)+normalise
+//   - weight packing (stem BN fold + tap packing, temporal BN fold, bf16 cast)
+// One warp owns one embedding row; every global access is a 128-bit (or the
+// widest aligned) coalesced vector access.
+#include "kws_common.cuh"
+#include "../../include/kws_b200.h"
+
+namespace kws {
+
+constexpr int MAX_LAYERS = 64;
+struct LayerIdx {
+  int32_t v[MAX_LAYERS];
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// ---------------------------------------------------------------------------
+// rows: x fp32 [B,Cin,T,D] -> out 16-bit [C, B, T, D]
+// NORMALIZE: out = fp16(x * mask / max(||x||, eps)); else out = bf16(x)
+// ---------------------------------------------------------------------------
+constexpr int ROW_MAX_V4 = 16;  // D <= 2048
+
+template <bool NORMALIZE>
+__global__ void __launch_bounds__(256) rows_kernel(const float* __restrict__ x, int B, int Cin, int T, int D,
+                                                   LayerIdx lidx, int C, const float* __restrict__ mask,
+                                                   float eps, uint16_t* __restrict__ out) {
+  const int warps_per_block = blockDim.x >> 5;
+  const long long n_rows = (long long)C * B * T;
+  const int lane = threadIdx.x & 31;
+  const int nv4 = D >> 2;
+  for (long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < n_rows;
+       row += (long long)gridDim.x * warps_per_block) {
+    const int t = (int)(row % T);
+    const int b = (int)((row / T) % B);
+    const int c = (int)(row / ((long long)T * B));
+    const float4* src = reinterpret_cast<const float4*>(x + (((long long)b * Cin + lidx.v[c]) * T + t) * D);
+    float4 v[ROW_MAX_V4];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < ROW_MAX_V4; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nv4) {
+        v[i] = ldg_stream(src + idx);
+        ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+      }
+    }
+    float scale = 1.f;
+    if (NORMALIZE) {
+      ss = warp_sum(ss);
+      const float m = mask ? mask[((long long)b * C + c) * T + t] : 1.f;
+      scale = m / fmaxf(sqrtf(ss), eps);
+    }
+    uint2* dst = reinterpret_cast<uint2*>(out + row * D);
+#pragma unroll
+    for (int i = 0; i < ROW_MAX_V4; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nv4) {
+        uint2 o;
+        if (NORMALIZE) {
+          o.x = pack_half2(v[i].x * scale, v[i].y * scale);
+          o.y = pack_half2(v[i].z * scale, v[i].w * scale);
+        } else {
+          o.x = pack_bf162(v[i].x, v[i].y);
+          o.y = pack_bf162(v[i].z, v[i].w);
+        }
+        dst[idx] = o;
+      }
+    }
+  }
+}
+
+static int launch_rows(bool normalize, const float* x, int B, int Cin, int T, int D, const int32_t* layer_idx,
+                       int C, const float* mask, float eps, void* out, cudaStream_t st) {
+  KWS_CHECK_ARG(x && out && layer_idx, "rows: null pointer");
+  KWS_CHECK_ARG(B > 0 && Cin > 0 && T > 0 && C > 0, "rows: non-positive dimension");
+  KWS_CHECK_ARG(C <= MAX_LAYERS, "rows: C=%d > %d", C, MAX_LAYERS);
+  KWS_CHECK_ARG(D % 8 == 0 && D <= ROW_MAX_V4 * 128, "rows: D=%d must be a multiple of 8 and <= %d", D,
+                ROW_MAX_V4 * 128);
+  KWS_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                "rows: pointers must be 16-byte aligned");
+  LayerIdx li;
+  for (int i = 0; i < C; ++i) {
+    KWS_CHECK_ARG(layer_idx[i] >= 0 && layer_idx[i] < Cin, "rows: layer_idx[%d]=%d out of [0,%d)", i,
+                  layer_idx[i], Cin);
+    li.v[i] = layer_idx[i];
+  }
+  const long long n_rows = (long long)C * B * T;
+  const int wpb = 8;
+  long long blocks = (n_rows + wpb - 1) / wpb;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (normalize)
+    rows_kernel<true><<<(int)blocks, wpb * 32, 0, st>>>(x, B, Cin, T, D, li, C, mask, eps, (uint16_t*)out);
+  else
+    rows_kernel<false><<<(int)blocks, wpb * 32, 0, st>>>(x, B, Cin, T, D, li, C, nullptr, eps, (uint16_t*)out);
+  KWS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// LEF temporal projector.  proj fp32 [C,B,T,P] -> out fp16 [C,B,T2,P]
+// block = (tile of TT output frames, b, c); conv+BN rows staged in smem.
+// ---------------------------------------------------------------------------
+constexpr int TT = 32;  // pooled frames per block -> 2*TT+1 conv rows, 2*TT+3 input rows
+
+__global__ void __launch_bounds__(256) temporal_kernel(const float* __restrict__ proj, int C, int B, int T, int P,
+                                                       int T2, const float* __restrict__ wf,
+                                                       const float* __restrict__ bf, const float* __restrict__ mask,
+                                                       float eps, __half* __restrict__ out) {
+  extern __shared__ __align__(16) float sm[];
+  const int n_in = 2 * TT + 3, n_y = 2 * TT + 1;
+  float* s_w = sm;                  // [3][P][P]
+  float* s_x = s_w + 3 * P * P;     // [n_in][P]
+  float* s_y = s_x + n_in * P;      // [n_y][P]
+  const int c = blockIdx.z, b = blockIdx.y, t2_0 = blockIdx.x * TT;
+  const int tid = threadIdx.x;
+  const float* w_c = wf + (size_t)c * 3 * P * P;
+  for (int i = tid; i < 3 * P * P; i += blockDim.x) s_w[i] = w_c[i];
+  // input rows t = 2*t2_0 - 2 ... 2*t2_0 + 2*TT  (zero outside [0,T): Conv1d zero padding)
+  const float* x_cb = proj + ((size_t)c * B + b) * T * P;
+  const int t_in0 = 2 * t2_0 - 2;
+  for (int i = tid; i < n_in * P; i += blockDim.x) {
+    const int t = t_in0 + i / P;
+    s_x[i] = (t >= 0 && t < T) ? x_cb[(size_t)t * P + (i % P)] : 0.f;
+  }
+  __syncthreads();
+  // conv rows y[r] <-> t = 2*t2_0 - 1 + r, r in [0, n_y)
+  const int groups = blockDim.x / P;  // threads sharing one output channel stride over rows
+  const int po = tid % P, g = tid / P;
+  if (g < groups) {
+    const float bias = bf[c * P + po];
+    for (int r0 = g; r0 < n_y; r0 += groups * 4) {
+      float acc[4] = {bias, bias, bias, bias};
+      for (int kk = 0; kk < 3; ++kk) {
+        const float* wk = s_w + kk * P * P + po;
+        for (int pi = 0; pi < P; ++pi) {
+          const float w = wk[pi * P];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int r = r0 + q * groups;
+            if (r < n_y) acc[q] = fmaf(w, s_x[(r + kk) * P + pi], acc[q]);
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r = r0 + q * groups;
+        if (r < n_y) s_y[r * P + po] = acc[q];
+      }
+    }
+  }
+  __syncthreads();
+  // MaxPool1d(3,2,1) (pads with -inf), L2 normalise over P, mask, fp16
+  const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+  for (int q = warp; q < TT; q += nwarps) {
+    const int t2 = t2_0 + q;
+    if (t2 >= T2) break;
+    float ss = 0.f;
+    float vals[8];  // P <= 256
+    int nv = 0;
+    for (int p = lane; p < P; p += 32, ++nv) {
+      float m = -INFINITY;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const int t = 2 * t2 - 1 + d;
+        if (t >= 0 && t < T) m = fmaxf(m, s_y[(2 * q + d) * P + p]);
+      }
+      vals[nv] = m;
+      ss += m * m;
+    }
+    ss = warp_sum(ss);
+    const float mk = mask ? mask[((size_t)b * C + c) * T2 + t2] : 1.f;
+    const float scale = mk / fmaxf(sqrtf(ss), eps);
+    __half* o = out + (((size_t)c * B + b) * T2 + t2) * P;
+    nv = 0;
+    for (int p = lane; p < P; p += 32, ++nv) o[p] = __float2half_rn(vals[nv] * scale);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// weight packing
+// ---------------------------------------------------------------------------
+__global__ void pack_stem_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, const float* __restrict__ mean,
+                                 const float* __restrict__ var, float eps, int C, int G, __half* __restrict__ wp,
+                                 float* __restrict__ bias) {
+  const int total = G * 49 * 2 * 64 * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int e = i & 7, oc = (i >> 3) & 63, chunk = (i >> 9) & 1;
+    const int tap = (i >> 10) % 49, g = (i >> 10) / 49;
+    const int ch = g * 16 + chunk * 8 + e;
+    float v = 0.f;
+    if (ch < C) {
+      const float s = gamma[oc] / sqrtf(var[oc] + eps);
+      v = w[((size_t)oc * C + ch) * 49 + tap] * s;
+    }
+    wp[i] = __float2half_rn(v);
+  }
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 64) bias[i] = beta[i] - mean[i] * gamma[i] / sqrtf(var[i] + eps);
+}
+
+__global__ void fold_temporal_kernel(const float* __restrict__ w, const float* __restrict__ cb,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                                     int C, int P, float* __restrict__ wf, float* __restrict__ bf) {
+  const int total = C * 3 * P * P;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int po = i % P, pi = (i / P) % P, kk = (i / (P * P)) % 3, c = i / (3 * P * P);
+    const float s = gamma[c * P + po] / sqrtf(var[c * P + po] + eps);
+    wf[i] = w[(((size_t)c * P + po) * P + pi) * 3 + kk] * s;
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < C * P; i += gridDim.x * blockDim.x) {
+    const float s = gamma[i] / sqrtf(var[i] + eps);
+    bf[i] = (cb[i] - mean[i]) * s + beta[i];
+  }
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    d[i] = __float2bfloat16_rn(s[i]);
+}
+
+// ---------------------------------------------------------------------------
+// scores + top-k
+// ---------------------------------------------------------------------------
+__global__ void scores_kernel(const float* __restrict__ logits, const float* __restrict__ hw, size_t n,
+                              float thr, float* __restrict__ scores, uint8_t* __restrict__ det) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float2 l = reinterpret_cast<const float2*>(logits)[i];
+    const float m = fmaxf(l.x, l.y);
+    const float e0 = expf(l.x - m), e1 = expf(l.y - m);
+    float s = e1 / (e0 + e1);
+    if (hw) s *= hw[i];
+    scores[i] = s;
+    if (det) det[i] = s >= thr ? 1 : 0;
+  }
+}
+
+// one block per utterance; k rounds of block-wide arg-max over the candidates
+// (k is small: the reference uses recall@{1..200}); ties -> lower id first.
+__global__ void __launch_bounds__(256) topk_kernel(const float* __restrict__ scores, const int32_t* __restrict__ ids,
+                                                   int n, int U, int id_offset, int k, float* __restrict__ os,
+                                                   int32_t* __restrict__ oi) {
+  extern __shared__ unsigned long long s_taken[];  // bitmap of taken candidates
+  __shared__ float s_best[8];
+  __shared__ int s_bid[8], s_bpos[8];
+  const int u = blockIdx.x, tid = threadIdx.x;
+  const int words = (n + 63) / 64;
+  for (int i = tid; i < words; i += blockDim.x) s_taken[i] = 0ull;
+  __syncthreads();
+  for (int r = 0; r < k; ++r) {
+    float best = -INFINITY;
+    int bid = 0x7fffffff, bpos = -1;
+    for (int c = tid; c < n; c += blockDim.x) {
+      if ((s_taken[c >> 6] >> (c & 63)) & 1ull) continue;
+      const float v = scores[(size_t)c * U + u];
+      const int id = ids ? ids[(size_t)c * U + u] : id_offset + c;
+      if (bpos < 0 || v > best || (v == best && id < bid)) best = v, bid = id, bpos = c;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oid = __shfl_xor_sync(0xffffffffu, bid, o);
+      const int op = __shfl_xor_sync(0xffffffffu, bpos, o);
+      if (op >= 0 && (bpos < 0 || ov > best || (ov == best && oid < bid))) best = ov, bid = oid, bpos = op;
+    }
+    if ((tid & 31) == 0) s_best[tid >> 5] = best, s_bid[tid >> 5] = bid, s_bpos[tid >> 5] = bpos;
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+        if (s_bpos[w] >= 0 && (bpos < 0 || s_best[w] > best || (s_best[w] == best && s_bid[w] < bid)))
+          best = s_best[w], bid = s_bid[w], bpos = s_bpos[w];
+      }
+      if (bpos >= 0) {
+        s_taken[bpos >> 6] |= 1ull << (bpos & 63);
+        os[(size_t)r * U + u] = best;
+        oi[(size_t)r * U + u] = bid;
+      } else {  // fewer candidates than k
+        os[(size_t)r * U + u] = -INFINITY;
+        oi[(size_t)r * U + u] = -1;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace kws
+
+using namespace kws;
+
+extern "C" {
+
+int kws_normalize_rows(const float* x, int B, int Cin, int T, int D, const int32_t* layer_idx, int C,
+                       const float* mask, float eps, void* out_f16, void* stream) {
+  return launch_rows(true, x, B, Cin, T, D, layer_idx, C, mask, eps, out_f16, (cudaStream_t)stream);
+}
+
+int kws_cast_rows_bf16(const float* x, int B, int Cin, int T, int D, const int32_t* layer_idx, int C,
+                       void* out_bf16, void* stream) {
+  return launch_rows(false, x, B, Cin, T, D, layer_idx, C, nullptr, 0.f, out_bf16, (cudaStream_t)stream);
+}
+
+int kws_temporal(const float* proj, int C, int B, int T, int P, const float* w_folded, const float* b_folded,
+                 const float* mask, float eps, void* out_f16, void* stream) {
+  KWS_CHECK_ARG(proj && w_folded && b_folded && out_f16, "temporal: null pointer");
+  KWS_CHECK_ARG(C > 0 && B > 0 && T > 0, "temporal: non-positive dimension");
+  KWS_CHECK_ARG(P > 0 && P <= 128 && 256 % P == 0, "temporal: P=%d must divide 256 and be <= 128", P);
+  KWS_CHECK_ARG(B <= 65535 && C <= 65535, "temporal: B,C must be <= 65535 per launch");
+  const int T2 = (T + 1) / 2;
+  const size_t smem = sizeof(float) * ((size_t)3 * P * P + (size_t)(2 * TT + 3) * P + (size_t)(2 * TT + 1) * P);
+  KWS_CHECK_ARG(smem <= 200 * 1024, "temporal: P=%d needs %zu bytes of shared memory", P, smem);
+  if (smem > 48 * 1024)
+    KWS_CUDA(cudaFuncSetAttribute(temporal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((T2 + TT - 1) / TT, B, C);
+  temporal_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(proj, C, B, T, P, T2, w_folded, b_folded, mask, eps,
+                                                            (__half*)out_f16);
+  KWS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+size_t kws_stem_weight_bytes(int C) { return (size_t)((C + 15) / 16) * 49 * 2 * 64 * 8 * sizeof(uint16_t); }
+
+int kws_pack_stem_weights(const float* conv_w, const float* gamma, const float* beta, const float* mean,
+                          const float* var, float eps, int C, void* w_packed, float* bias, void* stream) {
+  KWS_CHECK_ARG(conv_w && gamma && beta && mean && var && w_packed && bias, "pack_stem: null pointer");
+  KWS_CHECK_ARG(C > 0 && C <= 64, "pack_stem: C=%d out of (0,64]", C);
+  const int G = (C + 15) / 16;
+  pack_stem_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(conv_w, gamma, beta, mean, var, eps, C, G,
+                                                         (__half*)w_packed, bias);
+  KWS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int kws_fold_temporal_weights(const float* conv_w, const float* conv_b, const float* gamma, const float* beta,
+                              const float* mean, const float* var, float eps, int C, int P, float* w_folded,
+                              float* b_folded, void* stream) {
+  KWS_CHECK_ARG(conv_w && conv_b && gamma && beta && mean && var && w_folded && b_folded,
+                "fold_temporal: null pointer");
+  KWS_CHECK_ARG(C > 0 && P > 0, "fold_temporal: non-positive dimension");
+  fold_temporal_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(conv_w, conv_b, gamma, beta, mean, var, eps, C, P,
+                                                             w_folded, b_folded);
+  KWS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int kws_cast_f32_to_bf16(const float* src, void* dst_bf16, size_t n, void* stream) {
+  KWS_CHECK_ARG(src && dst_bf16, "cast: null pointer");
+  if (n == 0) return 0;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 4096) blocks = 4096;
+  cast_bf16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst_bf16, n);
+  KWS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int kws_scores(const float* logits, const float* hotword_mask, size_t n, float threshold, float* scores,
+               uint8_t* detections, void* stream) {
+  KWS_CHECK_ARG(logits && scores, "scores: null pointer");
+  if (n == 0) return 0;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 4096) blocks = 4096;
+  scores_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(logits, hotword_mask, n, threshold, scores,
+                                                              detections);
+  KWS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int kws_topk(const float* scores, const int32_t* ids, int n_cand, int U, int id_offset, int k, float* out_scores,
+             int32_t* out_ids, void* stream) {
+  KWS_CHECK_ARG(scores && out_scores && out_ids, "topk: null pointer");
+  KWS_CHECK_ARG(n_cand > 0 && U > 0 && k > 0 && k <= 1024, "topk: need n_cand>0, U>0, 0<k<=1024");
+  const size_t smem = (size_t)((n_cand + 63) / 64) * sizeof(unsigned long long);
+  KWS_CHECK_ARG(smem <= 48 * 1024, "topk: n_cand=%d too large for one pass (max %d)", n_cand, 48 * 1024 * 8);
+  topk_kernel<<<U, 256, smem, (cudaStream_t)stream>>>(scores, ids, n_cand, U, id_offset, k, out_scores, out_ids);
+  KWS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,158 @@
+"""Host-side driver of the B200 hot path: weight packing and the batched
+compress -> similarity -> stem pipeline over K keywords x U utterances.
+
+This is the batched replacement of the per-group Python loop in the reference's
+``test_step`` (src/efficient_kws/model.py:748-802): keywords are compressed
+once into a resident fp16 bank, every utterance is compressed once, and all
+K x U pairs stream through the similarity GEMM and the stem in pair chunks.
+All arithmetic is in libkws_b200.so (see ``ops``); nothing here computes on CPU.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Iterator, Mapping, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+
+STEM_KEY = "model.feature_extractor.embedder.embedder."
+
+
+@dataclass
+class PackedWeights:
+    """Device-resident, kernel-ready weights of one checkpoint (inference only:
+    BatchNorm layers are folded with their running statistics)."""
+
+    variant: str  # "L" | "LE" | "LEF"
+    C: int
+    D: int
+    P: int
+    w1: Optional[torch.Tensor] = None  # bf16 [C,H,D]
+    b1: Optional[torch.Tensor] = None  # fp32 [C,H]
+    w2: Optional[torch.Tensor] = None  # bf16 [C,P,H]
+    b2: Optional[torch.Tensor] = None  # fp32 [C,P]
+    wt: Optional[torch.Tensor] = None  # fp32 [C,3,P,P]  temporal conv, BN folded
+    bt: Optional[torch.Tensor] = None  # fp32 [C,P]
+    stem_w: Optional[torch.Tensor] = None  # fp16 [G,49,2,64,8]
+    stem_b: Optional[torch.Tensor] = None  # fp32 [64]
+
+    @property
+    def Dk(self) -> int:
+        return self.D if self.variant == "L" else self.P
+
+
+def pack_weights(sd: Mapping[str, torch.Tensor], variant: str, C: int, D: int, P: int,
+                 device: torch.device) -> PackedWeights:
+    """Pack a reference-keyed state_dict (projector.{i}.{0,2}.*, time_projector.{i}.{0,1}.*,
+    model.feature_extractor.embedder.embedder.*) for the kernels."""
+    def dev(k):
+        return sd[k].detach().to(device=device, dtype=torch.float32)
+
+    pw = PackedWeights(variant=variant, C=C, D=D, P=P)
+    if variant in ("LE", "LEF"):
+        pw.w1 = ops.cast_bf16(torch.stack([dev(f"projector.{i}.0.weight") for i in range(C)]))
+        pw.b1 = torch.stack([dev(f"projector.{i}.0.bias") for i in range(C)]).contiguous()
+        pw.w2 = ops.cast_bf16(torch.stack([dev(f"projector.{i}.2.weight") for i in range(C)]))
+        pw.b2 = torch.stack([dev(f"projector.{i}.2.bias") for i in range(C)]).contiguous()
+    if variant == "LEF":
+        st = lambda name: torch.stack([dev(f"time_projector.{i}.{name}") for i in range(C)])
+        pw.wt, pw.bt = ops.fold_temporal_weights(st("0.weight"), st("0.bias"), st("1.weight"), st("1.bias"),
+                                                 st("1.running_mean"), st("1.running_var"))
+    if STEM_KEY + "convolution.weight" in sd:
+        pw.stem_w, pw.stem_b = ops.pack_stem_weights(
+            dev(STEM_KEY + "convolution.weight"), dev(STEM_KEY + "normalization.weight"),
+            dev(STEM_KEY + "normalization.bias"), dev(STEM_KEY + "normalization.running_mean"),
+            dev(STEM_KEY + "normalization.running_var"))
+    return pw
+
+
+class KWSEngine:
+    """compress / similarity / stem over batches, with bounded workspaces."""
+
+    def __init__(self, weights: PackedWeights, workspace_bytes: int = 8 << 30):
+        self.w = weights
+        self.workspace_bytes = int(workspace_bytes)
+
+    # -- stage 1: per-layer compression -> normalised fp16 operands [C,B,T',Dk] ------
+    def out_frames(self, T: int) -> int:
+        return (T + 1) // 2 if self.w.variant == "LEF" else T
+
+    def compress(self, x: torch.Tensor, mask: Optional[torch.Tensor],
+                 layer_idx: Optional[Sequence[int]] = None) -> torch.Tensor:
+        """x fp32 [B,Cin,T,D]; mask fp32 [B,C,T'] at the resolution the similarity sees
+        (T for L/LE, ceil(T/2) for LEF) or None -> fp16 [C,B,T',Dk]."""
+        w = self.w
+        B, Cin, T, D = x.shape
+        if D != w.D:
+            raise ops.KWSError(f"embedding dim {D} != model embedding_dim {w.D}")
+        if layer_idx is None:
+            layer_idx = list(range(w.C))
+        if len(layer_idx) != w.C:
+            raise ops.KWSError(f"need {w.C} layer indices, got {len(layer_idx)}")
+        x = x.contiguous()
+        if x.dtype != torch.float32:
+            x = x.float()
+        if mask is not None:
+            mask = mask.to(torch.float32).contiguous()
+        if w.variant == "L":
+            return ops.normalize_rows(x, layer_idx, mask)
+        T2 = self.out_frames(T)
+        out = torch.empty((w.C, B, T2, w.P), dtype=torch.float16, device=x.device)
+        H = w.w1.shape[1]
+        per_item = w.C * T * (D + H) * 2 + w.C * T * w.P * 4
+        step = max(1, min(B, self.workspace_bytes // max(per_item, 1)))
+        for b0 in range(0, B, step):
+            b1 = min(B, b0 + step)
+            xb = ops.cast_rows_bf16(x[b0:b1], layer_idx)
+            mb = mask[b0:b1].contiguous() if mask is not None else None
+            if w.variant == "LE":
+                o = ops.mlp(xb, b1 - b0, T, w.w1, w.b1, w.w2, w.b2, mb, ops.MLP_OUT_NORM_F16)
+            else:
+                proj = ops.mlp(xb, b1 - b0, T, w.w1, w.b1, w.w2, w.b2, None, ops.MLP_OUT_RAW_F32)
+                o = ops.temporal(proj, w.wt, w.bt, mb)
+            if step >= B:
+                return o
+            out[:, b0:b1] = o
+        return out
+
+    # -- stage 2+3 over pair chunks -----------------------------------------------------
+    def pair_chunks(self, K: int, U: int, Tk: int, Tu: int, max_pairs: int) -> Iterator[Tuple[int, int, int, int]]:
+        """Tile the K x U pair grid into (k0,k1,u0,u1) blocks of at most max_pairs pairs:
+        whole keyword ranges per utterance block so the keyword slab is reused."""
+        max_pairs = max(1, max_pairs)
+        ub = max(1, min(U, max_pairs // max(1, min(K, max_pairs))))
+        kb = max(1, min(K, max_pairs // ub))
+        for u0 in range(0, U, ub):
+            for k0 in range(0, K, kb):
+                yield k0, min(K, k0 + kb), u0, min(U, u0 + ub)
+
+    def hot_path(self, kwd_n: torch.Tensor, utt_n: torch.Tensor, out_mode: int, max_pairs: int = 1024,
+                 consume: Optional[Callable] = None, bufs: Optional[dict] = None):
+        """Similarity + stem for all pairs, chunked.  ``consume(k0,k1,u0,u1,stem_out)`` receives the
+        stem activation of each chunk ([pairs,64,Ho,Wo], pair = (k-k0)*(u1-u0) + (u-u0));
+        intermediate buffers are reused across chunks (``bufs``)."""
+        Cc, K, Tk, Dk = kwd_n.shape
+        _, U, Tu, _ = utt_n.shape
+        bufs = bufs if bufs is not None else {}
+        n = 0
+        for k0, k1, u0, u1 in self.pair_chunks(K, U, Tk, Tu, max_pairs):
+            kk = kwd_n[:, k0:k1].contiguous() if (k0, k1) != (0, K) else kwd_n
+            uu = utt_n[:, u0:u1].contiguous() if (u0, u1) != (0, U) else utt_n
+            np_ = (k1 - k0) * (u1 - u0)
+            key16 = ("f16", np_, Cc, Tk, Tu)
+            if key16 not in bufs:
+                bufs[key16] = torch.empty((k1 - k0, u1 - u0, Cc, Tk, ops.pitch_for(Tu)), dtype=torch.float16,
+                                          device=kwd_n.device)
+            _, f16 = ops.sim(kk, uu, want_f32=False, want_f16=True, out_f16=bufs[key16])
+            keyo = ("stem", np_, Tk, Tu, out_mode)
+            if keyo not in bufs:
+                Ho, Wo = (Tk + 1) // 2, (Tu + 1) // 2
+                shape = (np_, 64, Ho, Wo) if out_mode == ops.STEM_OUT_NCHW_F32 else (np_, Ho, Wo, 64)
+                bufs[keyo] = torch.empty(shape, dtype=torch.float32 if out_mode == ops.STEM_OUT_NCHW_F32
+                                         else torch.bfloat16, device=kwd_n.device)
+            st = ops.stem(f16, Tu, self.w.stem_w, self.w.stem_b, out_mode, out=bufs[keyo])
+            if consume is not None:
+                consume(k0, k1, u0, u1, st)
+            n += np_
+        return n

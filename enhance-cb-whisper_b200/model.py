@@ -1,0 +1,313 @@
+"""Drop-in mirror of the reference ``efficient_kws`` model interface, backed by
+the sm_100a kernels.
+
+``KWSModelB200`` accepts the same constructor arguments as the reference
+``KWSModel`` (src/efficient_kws/model.py:19-59, dead hyper-parameters
+included), exposes the same sub-module names -- hence the same ``state_dict``
+keys, so reference checkpoints load unchanged -- and the same
+``forward(kwd_features, utt_features, labels, kwd_mask, utt_mask) -> KWSOutput``
+(model.py:129-208).  Only ``forward`` differs: projection, similarity, masking
+and the ResNet stem run in libkws_b200.so; the ResNet body and the Linear head
+are the unmodified HuggingFace / torch modules (cuDNN / cuBLAS), as in the
+reference.
+
+Inference only: BatchNorm layers are folded with their running statistics, so
+``forward`` refuses to run in training mode rather than silently mis-compute.
+
+When ``pytorch_lightning`` and the reference package are importable, use
+``enhance_cb_whisper_b200.lightning.KWSModelB200`` instead (same forward, but
+subclassing the reference LightningModule so that ``run_efficient_kws.py`` and
+its YAML configs keep working with a one-line ``class_path`` change).
+"""
+from __future__ import annotations
+
+import copy
+import re
+from dataclasses import dataclass
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .engine import KWSEngine, PackedWeights, pack_weights
+
+
+@dataclass
+class KWSOutput:
+    """Same fields as the reference dataclass (src/efficient_kws/utils.py:5-13)."""
+
+    logits: torch.Tensor
+    features: Optional[torch.Tensor]
+    loss: Optional[torch.Tensor] = None
+    logits_alt: Optional[torch.Tensor] = None
+    loss_alt: Optional[dict] = None
+
+
+class Resnet(nn.Module):
+    """HF ResNet feature extractor + Linear head with the attribute names of the
+    reference wrapper (src/efficient_kws/resnet.py:7-58) so that state_dict keys
+    (``feature_extractor.*``, ``classifier.1.*``) are identical."""
+
+    _VERSIONS = {
+        "resnet-18": ("basic", [64, 128, 256, 512], [2, 2, 2, 2]),
+        "resnet-34": ("basic", [64, 128, 256, 512], [3, 4, 6, 3]),
+    }
+
+    def __init__(self, num_channels: int, num_classes: Optional[int] = None, version: str = "resnet-50"):
+        super().__init__()
+        from transformers import ResNetConfig, ResNetModel
+
+        self.num_channels, self.num_classes, self.version = num_channels, num_classes, version
+        cfg = ResNetConfig()
+        if version in self._VERSIONS:
+            cfg.layer_type, cfg.hidden_sizes, cfg.depths = self._VERSIONS[version]
+        cfg.num_channels = num_channels
+        if num_classes is not None:
+            cfg.num_labels = num_classes
+        self.config = cfg
+        self.feature_extractor = ResNetModel(cfg)
+        if num_classes is not None:
+            self.classifier = nn.Sequential(nn.Flatten(1, -1), nn.Linear(cfg.hidden_sizes[-1], cfg.num_labels))
+
+    def forward(self, input_features: torch.Tensor) -> torch.Tensor:  # stock path (not used by B200 forward)
+        pooled = self.feature_extractor(input_features).pooler_output
+        return self.classifier(torch.flatten(pooled, 1))
+
+
+def run_body(resnet: nn.Module, stem_activation: torch.Tensor) -> torch.Tensor:
+    """Everything after the stem conv/BN/ReLU, on the unmodified HF modules: max-pool, residual
+    stages, adaptive avg-pool (HF modeling_resnet.py) and the Linear head (resnet.py:42-58).
+    Works on the reference's own Resnet wrapper as well (same attribute names)."""
+    fe = resnet.feature_extractor
+    x = fe.embedder.pooler(stem_activation)
+    x = fe.encoder(x).last_hidden_state
+    x = fe.pooler(x)
+    return resnet.classifier(torch.flatten(x, 1).float())
+
+
+class _HParams(dict):
+    __getattr__ = dict.__getitem__
+    __setattr__ = dict.__setitem__
+
+
+class B200ForwardMixin:
+    """The B200 ``forward`` shared by the standalone module and the Lightning
+    subclass.  Expects ``self.hparams`` (variant flags), ``self.model`` (Resnet)
+    and, for LE/LEF, ``self.projector`` / ``self.time_projector``."""
+
+    # options (set through **kwargs ``b200_*`` or attributes)
+    b200_body_dtype: str = "float32"  # "float32" (parity) | "bfloat16" (throughput, channels_last)
+    b200_return_features: bool = True  # materialise KWSOutput.features (fp32) like the reference
+    b200_layer_idx: Optional[Sequence[int]] = None  # explicit layer selection into the given stack
+
+    def _b200_init(self):
+        self._packed: Optional[PackedWeights] = None
+        self._packed_key = None
+        self._engine: Optional[KWSEngine] = None
+        self._body_lowp = None
+
+    # ---- variant / weights ---------------------------------------------------------
+    @property
+    def variant(self) -> str:
+        hp = self.hparams
+        if not hp.proj_mlp:
+            return "L"
+        return "LEF" if hp.frames_conv else "LE"
+
+    def _weights_key(self, device):
+        vers = tuple(int(p._version) for p in self.parameters()) + tuple(int(b._version) for b in self.buffers())
+        return (str(device), hash(vers))
+
+    def prepare(self, device: Optional[torch.device] = None) -> KWSEngine:
+        """Fold BN / cast / pack the hot-path weights for the kernels (once per checkpoint;
+        re-done automatically when parameters are modified in place or moved)."""
+        if device is None:
+            device = next(self.parameters()).device
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise ops.KWSError("KWSModelB200 runs on CUDA only: move the module to a B200 (no CPU fallback)")
+        key = self._weights_key(device)
+        if self._engine is None or self._packed_key != key:
+            hp = self.hparams
+            sd = {k: v for k, v in self.state_dict().items()}
+            self._packed = pack_weights(sd, self.variant, hp.n_layers, hp.embedding_dim, hp.proj_mlp_units, device)
+            self._engine = KWSEngine(self._packed)
+            self._packed_key = key
+            self._body_lowp = None
+        return self._engine
+
+    def _body(self, stem_act: torch.Tensor) -> torch.Tensor:
+        if self.b200_body_dtype == "float32":
+            return run_body(self.model, stem_act)
+        if self._body_lowp is None:
+            m = copy.deepcopy(self.model).to(dtype=torch.bfloat16, memory_format=torch.channels_last)
+            m.classifier.float()
+            self._body_lowp = m.eval()
+        return run_body(self._body_lowp, stem_act)
+
+    # ---- the reference-facing call -------------------------------------------------
+    def forward(self, kwd_features: torch.Tensor, utt_features: torch.Tensor, labels: torch.Tensor = None,
+                kwd_mask: Optional[torch.Tensor] = None, utt_mask: Optional[torch.Tensor] = None) -> KWSOutput:
+        if self.training:
+            raise RuntimeError("KWSModelB200.forward is inference-only (BatchNorm folded with running statistics); "
+                               "call .eval() -- training stays on the reference PyTorch path")
+        if kwd_mask is None or utt_mask is None:
+            # the reference dereferences both masks unconditionally (model.py:187-191)
+            raise AttributeError("kwd_mask and utt_mask are required (reference forward calls .unsqueeze on them)")
+        hp = self.hparams
+        Cn = hp.n_layers
+        K, Ub = kwd_features.shape[0], utt_features.shape[0]
+        if Ub != 1 and Ub != K:
+            raise RuntimeError(f"utt_features batch {Ub} must be 1 or equal the keyword batch {K} "
+                               "(reference expands it to n_keywords, model.py:178)")
+        diag = Ub == K and K > 1
+        variant = self.variant
+        if variant == "L" and (kwd_features.shape[1] != Cn or utt_features.shape[1] != Cn):
+            # HF ResNetEmbeddings raises on a channel mismatch (modeling_resnet.py:71-75)
+            raise ValueError("Make sure that the channel dimension of the pixel values match with the one set in "
+                             "the configuration.")
+        layer_idx = list(self.b200_layer_idx) if self.b200_layer_idx is not None else list(range(Cn))
+        eng = self.prepare(kwd_features.device)
+        with torch.no_grad():
+            kwd_n = eng.compress(kwd_features, kwd_mask, layer_idx)
+            utt_n = eng.compress(utt_features, utt_mask, layer_idx)
+            f32, f16 = ops.sim(kwd_n, utt_n, want_f32=self.b200_return_features, want_f16=True, diag=diag)
+            Tu_s = utt_n.shape[2]
+            lowp = self.b200_body_dtype != "float32"
+            st = ops.stem(f16, Tu_s, eng.w.stem_w, eng.w.stem_b,
+                          ops.STEM_OUT_NHWC_BF16 if lowp else ops.STEM_OUT_NCHW_F32)
+            logits = self._body(st).float()
+        features = None
+        if f32 is not None:
+            features = f32 if diag else f32[:, 0]
+        loss = F.cross_entropy(logits, labels.view(-1)) if labels is not None else None
+        return KWSOutput(loss=loss, logits=logits, features=features, logits_alt=None,
+                         loss_alt={"loss_diag": None, "loss_resnet": loss})
+
+    def resnet_forward(self, input_features: torch.Tensor):
+        return self.model(input_features)
+
+    # ---- batched scoring (replacement of the test_step group loop) ------------------
+    @torch.no_grad()
+    def score(self, kwd_features, utt_features, kwd_mask, utt_mask, hotword_mask=None, max_pairs: int = 256,
+              threshold: Optional[float] = None):
+        """All K x U pairs -> (scores [K,U], detections uint8 [K,U], logits [K,U,2]).
+        score = softmax(logits)[:,1] * hotword_mask (model.py:783-795)."""
+        eng = self.prepare(kwd_features.device)
+        layer_idx = list(self.b200_layer_idx) if self.b200_layer_idx is not None else list(range(self.hparams.n_layers))
+        kwd_n = eng.compress(kwd_features, kwd_mask, layer_idx)
+        utt_n = eng.compress(utt_features, utt_mask, layer_idx)
+        return self.score_compressed(kwd_n, utt_n, hotword_mask, max_pairs, threshold)
+
+    @torch.no_grad()
+    def score_compressed(self, kwd_n, utt_n, hotword_mask=None, max_pairs: int = 256,
+                         threshold: Optional[float] = None):
+        eng = self.prepare(kwd_n.device)
+        K, U = kwd_n.shape[1], utt_n.shape[1]
+        logits = torch.empty((K, U, 2), dtype=torch.float32, device=kwd_n.device)
+        lowp = self.b200_body_dtype != "float32"
+
+        def consume(k0, k1, u0, u1, st):
+            logits[k0:k1, u0:u1] = self._body(st).float().view(k1 - k0, u1 - u0, 2)
+
+        eng.hot_path(kwd_n, utt_n, ops.STEM_OUT_NHWC_BF16 if lowp else ops.STEM_OUT_NCHW_F32, max_pairs, consume)
+        hw = None
+        if hotword_mask is not None:
+            hw = hotword_mask.to(logits.device, torch.float32).view(K, 1).expand(K, U).contiguous().view(-1)
+        thr = float(self.hparams.threshold if threshold is None else threshold)
+        sc, det = ops.scores(logits.view(-1, 2), hw, thr)
+        return sc.view(K, U), det.view(K, U), logits
+
+
+class KWSModelB200(B200ForwardMixin, nn.Module):
+    """Standalone (no Lightning) module with the reference constructor signature."""
+
+    def __init__(
+        self,
+        num_domains: int = 72,
+        sampling: str = "utterance-examples",
+        resample_every_epoch: bool = True,
+        kw_type: str = "tts",
+        kw_p: float = 0.5,
+        features_size: Tuple[int, int] = (160, 1000),
+        learn_features: bool = False,
+        load_embeddings: bool = True,
+        n_layers: int = 12,
+        pad_long_before_resize: bool = False,
+        kws_whisper_ckpt: str = "openai/whisper-large-v2",
+        embedding_dim: int = 1024,
+        features_with_conv: bool = False,
+        features_with_attn: bool = False,
+        frames_conv: bool = False,
+        proj_mlp: bool = False,
+        proj_mlp_units: int = 64,
+        batch_size: int = 1,
+        accumulate_grad_batches: int = 1,
+        learning_rate_sru: float = 1e-4,
+        learning_rate: float = 1e-4,
+        warmup_proportion: float = 0.0,
+        max_epochs: int = 200,
+        features_lr: float = 1e-4,
+        classifier_lr: float = 1e-4,
+        lr_step: int = 40,
+        weight_decay: float = 0.0,
+        beta_1: float = 0.9,
+        beta_2: float = 0.99,
+        condensed_dimension: str = "embeddings",
+        resnet_version: str = "resnet-50",
+        compile: bool = False,
+        threshold: float = 0.5,
+        task_type: str = "keyword-spotting",
+        diag_size: int = 5,
+        alpha_max_epochs: int = 10,
+        min_alpha: float = 0.1,
+        **kwargs,
+    ):
+        super().__init__()
+        hp = _HParams({k: v for k, v in locals().items() if k not in ("self", "kwargs", "__class__")})
+        for k, v in kwargs.items():
+            if k.startswith("b200_"):
+                setattr(self, k, v)
+            else:
+                hp[k] = v  # dead hyper-parameters of the YAMLs (sru_*, ...) are accepted and kept
+        object.__setattr__(self, "hparams", hp)
+        # sub-modules: same construction rules as the reference (model.py:71-124)
+        if not hp.learn_features:
+            self.model = Resnet(num_channels=hp.n_layers, num_classes=2)
+        elif hp.proj_mlp:
+            self.model = Resnet(num_channels=hp.n_layers, num_classes=2, version=hp.resnet_version)
+            self.projector = nn.ModuleList()
+            if hp.frames_conv:
+                self.time_projector = nn.ModuleList()
+            for _ in range(hp.n_layers):
+                self.projector.append(nn.Sequential(
+                    nn.Linear(hp.embedding_dim, hp.embedding_dim // 2), nn.ReLU(),
+                    nn.Linear(hp.embedding_dim // 2, hp.proj_mlp_units)))
+                if hp.frames_conv:
+                    self.time_projector.append(nn.Sequential(
+                        nn.Conv1d(hp.proj_mlp_units, hp.proj_mlp_units, kernel_size=3, stride=1, padding=1),
+                        nn.BatchNorm1d(hp.proj_mlp_units),
+                        nn.MaxPool1d(kernel_size=3, stride=2, padding=1)))
+        else:
+            # shipped L YAMLs (learn_features: true, proj_mlp: false) build no ResNet in the reference and
+            # fail at the first forward; fail at construction instead.
+            raise ValueError("learn_features=True with proj_mlp=False builds no classifier in the reference "
+                             "(model.py:71-85); use learn_features=False for the L variant")
+        self._b200_init()
+        self.eval()
+
+    @staticmethod
+    def remap_legacy_state_dict(state_dict: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """Legacy checkpoint key remap of the reference's on_load_checkpoint (model.py:931-952):
+        drop ``resnet.`` and insert ``feature_extractor.`` for model.embedder / model.encoder keys."""
+        if not any("resnet." in k for k in state_dict):
+            return dict(state_dict)
+        out = {}
+        for k, v in state_dict.items():
+            nk = k.replace("resnet.", "")
+            if re.search(r"(model.embedder|model.encoder)", nk):
+                nk = nk[:6] + "feature_extractor." + nk[6:]
+            out[nk] = v
+        return out

@@ -1,0 +1,223 @@
+"""Torch-tensor front end of the C ABI: allocates outputs with the caching
+allocator, checks shapes/devices, passes raw device pointers and the current
+CUDA stream to libkws_b200.so.  PyTorch is plumbing here (memory + streams);
+all arithmetic happens in the CUDA library.  CPU tensors are rejected -- there
+is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (MLP_OUT_NORM_F16, MLP_OUT_RAW_F32, PAIRS_ALL, PAIRS_DIAG, STEM_OUT_NCHW_F32,
+                   STEM_OUT_NHWC_BF16, KWSError, check)
+
+SIM_EPS = 1e-6  # reference src/efficient_kws/model.py:210
+BN_EPS = 1e-5
+
+
+def _cuda(t: Optional[torch.Tensor], name: str, dtype=None) -> int:
+    if t is None:
+        return 0
+    if not t.is_cuda:
+        raise KWSError(f"{name} must be a CUDA tensor (the kws_b200 path has no CPU fallback)")
+    if not t.is_contiguous():
+        raise KWSError(f"{name} must be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise KWSError(f"{name} must be {dtype}, got {t.dtype}")
+    return t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _layers(layer_idx: Sequence[int]):
+    arr = (C.c_int32 * len(layer_idx))(*[int(i) for i in layer_idx])
+    return arr
+
+
+def sm_count() -> int:
+    return _lib.load().kws_sm_count()
+
+
+# ---- once per checkpoint -----------------------------------------------------
+def pack_stem_weights(conv_w, gamma, beta, mean, var, eps: float = BN_EPS) -> Tuple[torch.Tensor, torch.Tensor]:
+    """-> (w_packed fp16 [G,49,2,64,8], bias fp32 [64])"""
+    lib = _lib.load()
+    Cc = conv_w.shape[1]
+    if tuple(conv_w.shape) != (64, Cc, 7, 7):
+        raise KWSError(f"stem conv weight must be [64,C,7,7], got {tuple(conv_w.shape)}")
+    args = [t.detach().float().contiguous() for t in (conv_w, gamma, beta, mean, var)]
+    G = (Cc + 15) // 16
+    wp = torch.empty((G, 49, 2, 64, 8), dtype=torch.float16, device=conv_w.device)
+    bias = torch.empty(64, dtype=torch.float32, device=conv_w.device)
+    check(lib.kws_pack_stem_weights(*[_cuda(a, "stem weight", torch.float32) for a in args], eps, Cc,
+                                    _cuda(wp, "w_packed"), _cuda(bias, "bias"), _stream()), "kws_pack_stem_weights")
+    return wp, bias
+
+
+def fold_temporal_weights(conv_w, conv_b, gamma, beta, mean, var, eps: float = BN_EPS):
+    """conv_w [C,P,P,3] ... -> (w_folded fp32 [C,3,P,P], b_folded fp32 [C,P])"""
+    lib = _lib.load()
+    Cc, P = conv_w.shape[0], conv_w.shape[1]
+    args = [t.detach().float().contiguous() for t in (conv_w, conv_b, gamma, beta, mean, var)]
+    wf = torch.empty((Cc, 3, P, P), dtype=torch.float32, device=conv_w.device)
+    bf = torch.empty((Cc, P), dtype=torch.float32, device=conv_w.device)
+    check(lib.kws_fold_temporal_weights(*[_cuda(a, "temporal weight", torch.float32) for a in args], eps, Cc, P,
+                                        _cuda(wf, "wf"), _cuda(bf, "bf"), _stream()), "kws_fold_temporal_weights")
+    return wf, bf
+
+
+def cast_bf16(src: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    src = src.detach().float().contiguous()
+    dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    check(lib.kws_cast_f32_to_bf16(_cuda(src, "src", torch.float32), _cuda(dst, "dst"), src.numel(), _stream()),
+          "kws_cast_f32_to_bf16")
+    return dst
+
+
+# ---- per batch of keywords / utterances ----------------------------------------
+def normalize_rows(x: torch.Tensor, layer_idx: Sequence[int], mask: Optional[torch.Tensor],
+                   eps: float = SIM_EPS) -> torch.Tensor:
+    """x fp32 [B,Cin,T,D] -> fp16 [C,B,T,D] (selected layers, L2-normalised, mask folded)."""
+    lib = _lib.load()
+    B, Cin, T, D = x.shape
+    Cc = len(layer_idx)
+    if mask is not None and tuple(mask.shape) != (B, Cc, T):
+        raise KWSError(f"mask must be [B,C,T]=({B},{Cc},{T}), got {tuple(mask.shape)}")
+    out = torch.empty((Cc, B, T, D), dtype=torch.float16, device=x.device)
+    check(lib.kws_normalize_rows(_cuda(x, "x", torch.float32), B, Cin, T, D, _layers(layer_idx), Cc,
+                                 _cuda(mask, "mask", torch.float32), eps, _cuda(out, "out"), _stream()),
+          "kws_normalize_rows")
+    return out
+
+
+def cast_rows_bf16(x: torch.Tensor, layer_idx: Sequence[int]) -> torch.Tensor:
+    """x fp32 [B,Cin,T,D] -> bf16 [C, B*T, D]."""
+    lib = _lib.load()
+    B, Cin, T, D = x.shape
+    Cc = len(layer_idx)
+    out = torch.empty((Cc, B * T, D), dtype=torch.bfloat16, device=x.device)
+    check(lib.kws_cast_rows_bf16(_cuda(x, "x", torch.float32), B, Cin, T, D, _layers(layer_idx), Cc,
+                                 _cuda(out, "out"), _stream()), "kws_cast_rows_bf16")
+    return out
+
+
+def mlp(x_bf16: torch.Tensor, B: int, T: int, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor,
+        b2: torch.Tensor, mask: Optional[torch.Tensor], out_mode: int, eps: float = SIM_EPS) -> torch.Tensor:
+    """x bf16 [C,B*T,D]; w1 bf16 [C,H,D]; b1 fp32 [C,H]; w2 bf16 [C,P,H]; b2 fp32 [C,P]
+    -> fp16 [C,B,T,P] (normalised) or fp32 [C,B,T,P] (raw)."""
+    lib = _lib.load()
+    Cc, R, D = x_bf16.shape
+    H, P = w1.shape[1], w2.shape[1]
+    if R != B * T:
+        raise KWSError(f"x rows {R} != B*T = {B * T}")
+    if tuple(w1.shape) != (Cc, H, D) or tuple(w2.shape) != (Cc, P, H):
+        raise KWSError("projector weight shapes do not match x")
+    hidden = torch.empty((Cc, R, H), dtype=torch.bfloat16, device=x_bf16.device)
+    out = torch.empty((Cc, B, T, P), dtype=torch.float16 if out_mode == MLP_OUT_NORM_F16 else torch.float32,
+                      device=x_bf16.device)
+    check(lib.kws_mlp(_cuda(x_bf16, "x", torch.bfloat16), Cc, B, T, D, H, P, _cuda(w1, "w1", torch.bfloat16),
+                      _cuda(b1, "b1", torch.float32), _cuda(w2, "w2", torch.bfloat16),
+                      _cuda(b2, "b2", torch.float32), _cuda(hidden, "hidden"),
+                      _cuda(mask, "mask", torch.float32), eps, out_mode, _cuda(out, "out"), _stream()), "kws_mlp")
+    return out
+
+
+def temporal(proj: torch.Tensor, wf: torch.Tensor, bf: torch.Tensor, mask: Optional[torch.Tensor],
+             eps: float = SIM_EPS) -> torch.Tensor:
+    """proj fp32 [C,B,T,P] -> fp16 [C,B,ceil(T/2),P]; mask fp32 [B,C,ceil(T/2)] or None."""
+    lib = _lib.load()
+    Cc, B, T, P = proj.shape
+    T2 = (T + 1) // 2
+    if mask is not None and tuple(mask.shape) != (B, Cc, T2):
+        raise KWSError(f"LEF mask must be at pooled resolution [B,C,ceil(T/2)]=({B},{Cc},{T2}), "
+                       f"got {tuple(mask.shape)}")
+    out = torch.empty((Cc, B, T2, P), dtype=torch.float16, device=proj.device)
+    check(lib.kws_temporal(_cuda(proj, "proj", torch.float32), Cc, B, T, P, _cuda(wf, "wf", torch.float32),
+                           _cuda(bf, "bf", torch.float32), _cuda(mask, "mask", torch.float32), eps,
+                           _cuda(out, "out"), _stream()), "kws_temporal")
+    return out
+
+
+# ---- per pair --------------------------------------------------------------------
+def pitch_for(Tu: int) -> int:
+    return (Tu + 7) // 8 * 8
+
+
+def sim(kwd_n: torch.Tensor, utt_n: torch.Tensor, want_f32: bool, want_f16: bool, diag: bool = False,
+        out_f32: Optional[torch.Tensor] = None, out_f16: Optional[torch.Tensor] = None):
+    """kwd_n fp16 [C,K,Tk,Dk], utt_n fp16 [C,U,Tu,Dk] ->
+    (features fp32 [K,U,C,Tk,Tu] | None, features fp16 [K,U,C,Tk,pitch] | None); DIAG drops the U axis."""
+    lib = _lib.load()
+    Cc, K, Tk, Dk = kwd_n.shape
+    Cu, U, Tu, Dku = utt_n.shape
+    if Cc != Cu or Dk != Dku:
+        raise KWSError(f"operand mismatch: kwd {tuple(kwd_n.shape)} vs utt {tuple(utt_n.shape)}")
+    lead = (K,) if diag else (K, U)
+    pitch = pitch_for(Tu)
+    f32 = f16 = None
+    if want_f32:
+        f32 = out_f32 if out_f32 is not None else torch.empty(lead + (Cc, Tk, Tu), dtype=torch.float32,
+                                                              device=kwd_n.device)
+    if want_f16:
+        # pitch padding is never read by the stem (it bounds-checks against Tu)
+        f16 = out_f16 if out_f16 is not None else torch.empty(lead + (Cc, Tk, pitch), dtype=torch.float16,
+                                                              device=kwd_n.device)
+    check(lib.kws_sim(_cuda(kwd_n, "kwd_n", torch.float16), _cuda(utt_n, "utt_n", torch.float16), Cc, K, U, Tk, Tu,
+                      Dk, PAIRS_DIAG if diag else PAIRS_ALL, _cuda(f32, "feat_f32", torch.float32),
+                      _cuda(f16, "feat_f16", torch.float16), pitch, _stream()), "kws_sim")
+    return f32, f16
+
+
+def stem(feat_f16: torch.Tensor, Tu: int, w_packed: torch.Tensor, bias: torch.Tensor, out_mode: int,
+         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """feat_f16 fp16 [..., C, Tk, pitch] -> NCHW fp32 [N,64,Ho,Wo] or channels_last bf16 (logical
+    shape [N,64,Ho,Wo], physical [N,Ho,Wo,64])."""
+    lib = _lib.load()
+    Cc, Tk, pitch = feat_f16.shape[-3:]
+    pairs = feat_f16.numel() // (Cc * Tk * pitch)
+    Ho, Wo = (Tk + 1) // 2, (Tu + 1) // 2
+    if out is None:
+        if out_mode == STEM_OUT_NCHW_F32:
+            out = torch.empty((pairs, 64, Ho, Wo), dtype=torch.float32, device=feat_f16.device)
+        else:
+            out = torch.empty((pairs, Ho, Wo, 64), dtype=torch.bfloat16, device=feat_f16.device)
+    check(lib.kws_stem(_cuda(feat_f16, "feat_f16", torch.float16), pairs, Cc, Tk, Tu, pitch,
+                       _cuda(w_packed, "w_packed", torch.float16), _cuda(bias, "bias", torch.float32), out_mode,
+                       _cuda(out, "out"), _stream()), "kws_stem")
+    if out_mode == STEM_OUT_NHWC_BF16:
+        return out.permute(0, 3, 1, 2)  # channels_last view
+    return out
+
+
+# ---- scores ------------------------------------------------------------------------
+def scores(logits: torch.Tensor, hotword_mask: Optional[torch.Tensor], threshold: float):
+    """logits fp32 [n,2] -> (scores fp32 [n], detections uint8 [n])"""
+    lib = _lib.load()
+    n = logits.shape[0]
+    logits = logits.float().contiguous()
+    sc = torch.empty(n, dtype=torch.float32, device=logits.device)
+    det = torch.empty(n, dtype=torch.uint8, device=logits.device)
+    if hotword_mask is not None:
+        hotword_mask = hotword_mask.float().contiguous()
+    check(lib.kws_scores(_cuda(logits, "logits", torch.float32), _cuda(hotword_mask, "hotword_mask", torch.float32),
+                         n, float(threshold), _cuda(sc, "scores"), _cuda(det, "det"), _stream()), "kws_scores")
+    return sc, det
+
+
+def topk(scores_cu: torch.Tensor, k: int, ids: Optional[torch.Tensor] = None, id_offset: int = 0):
+    """scores fp32 [n_cand,U] (+ ids int32 [n_cand,U]) -> (top scores [k,U], top ids int32 [k,U]);
+    ties broken by the lower id."""
+    lib = _lib.load()
+    n, U = scores_cu.shape
+    os_ = torch.empty((k, U), dtype=torch.float32, device=scores_cu.device)
+    oi = torch.empty((k, U), dtype=torch.int32, device=scores_cu.device)
+    check(lib.kws_topk(_cuda(scores_cu, "scores", torch.float32), _cuda(ids, "ids", torch.int32), n, U,
+                       int(id_offset), int(k), _cuda(os_, "out_scores"), _cuda(oi, "out_ids"), _stream()), "kws_topk")
+    return os_, oi

@@ -1,0 +1,14 @@
+"""Import shim: the package directory is named ``enhance-cb-whisper_b200`` (not a
+valid Python identifier); importing ``enhance_cb_whisper_b200`` loads it as a
+regular package (sub-modules included) from that directory."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "enhance-cb-whisper_b200")
+_spec = importlib.util.spec_from_file_location(
+    __name__, os.path.join(_dir, "__init__.py"), submodule_search_locations=[_dir]
+)
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules[__name__] = _mod
+_spec.loader.exec_module(_mod)

@@ -1,0 +1,162 @@
+/*
+ * kws_b200.h -- C ABI of the B200-native efficient_kws scoring path.
+ *
+ * The reference (Priberam/Enhance-CB-Whisper) has no native boundary: its hot
+ * path is the body of one nn.Module.forward (src/efficient_kws/model.py:129-221)
+ * plus the HuggingFace ResNet stem it calls (src/efficient_kws/resnet.py:38,53).
+ * Each entry point below replaces the stock PyTorch ops of one stage of that
+ * forward; the "replaces" note gives the reference lines.  The Python mirror of
+ * the reference interface (enhance-cb-whisper_b200/model.py) binds these with
+ * ctypes; INTEGRATION.md shows the stub a maintainer would add.
+ *
+ * Conventions
+ *  - every function returns int: 0 ok, <0 bad argument (see kws_last_error()),
+ *    >0 a cudaError_t raised while launching;
+ *  - all data pointers are DEVICE pointers owned by the caller, 16-byte aligned;
+ *    nothing is allocated, freed or synchronised inside the library;
+ *  - `stream` is a cudaStream_t passed as void*; work is enqueued on it;
+ *  - re-entrant from several host threads on different streams (the only global
+ *    state is a one-time driver entry-point lookup and cached device attributes);
+ *  - layouts are row-major with the last index contiguous.
+ *
+ * "Layer-major" operand layout: compressed keyword / utterance embeddings are
+ * kept as fp16 [C, B, T', Dk] (layer, item, frame, dim), L2-normalised over Dk
+ * with the 0/1 frame mask folded in as a row scale, so the similarity of a
+ * (keyword, utterance) pair in layer c is a plain K-major GEMM of two slabs.
+ */
+#ifndef KWS_B200_H_
+#define KWS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KWS_ABI_VERSION 1
+
+/* kws_mlp out_mode */
+#define KWS_MLP_OUT_NORM_F16 0 /* LE : fp16 [C,R,P], row-normalised * mask          */
+#define KWS_MLP_OUT_RAW_F32 1  /* LEF: fp32 [C,R,P], un-normalised (feeds kws_temporal) */
+
+/* kws_sim pair_mode */
+#define KWS_PAIRS_ALL 0
+#define KWS_PAIRS_DIAG 1
+
+/* kws_stem out_mode */
+#define KWS_STEM_OUT_NCHW_F32 0  /* fp32 [pairs,64,Ho,Wo]   (parity with the reference) */
+#define KWS_STEM_OUT_NHWC_BF16 1 /* bf16 [pairs,Ho,Wo,64]   (channels_last hand-off)    */
+
+int kws_abi_version(void);
+/* thread-local description of the last non-zero return value */
+const char* kws_last_error(void);
+/* number of SMs of the current device (grid sizing; 148 on B200) */
+int kws_sm_count(void);
+
+/* ---- once per checkpoint ------------------------------------------------ */
+
+/* Fold BatchNorm2d (eval) into the stem convolution and pack it for the
+ * tap-decomposed implicit GEMM.  Replaces nothing at run time; prepares
+ * model.feature_extractor.embedder.embedder.{convolution,normalization}
+ * (HF modeling_resnet.py:39-54 via src/efficient_kws/resnet.py:38).
+ *   conv_w fp32 [64,C,7,7]; gamma,beta,mean,var fp32 [64]
+ *   w_packed fp16 [G][49][2][64][8], G = ceil(C/16); channel = 16 g + 8 chunk + e
+ *   bias fp32 [64] = beta - mean * gamma / sqrt(var + eps)                     */
+int kws_pack_stem_weights(const float* conv_w, const float* gamma, const float* beta, const float* mean,
+                          const float* var, float eps, int C, void* w_packed, float* bias, void* stream);
+size_t kws_stem_weight_bytes(int C);
+
+/* Fold BatchNorm1d (eval) into the LEF temporal Conv1d.
+ * time_projector[i] = Conv1d(P,P,3,pad 1) -> BatchNorm1d -> MaxPool1d(3,2,1)
+ * (src/efficient_kws/model.py:107-124).
+ *   conv_w fp32 [C,P,P,3], conv_b/gamma/beta/mean/var fp32 [C,P]
+ *   w_folded fp32 [C,3,P(in),P(out)], b_folded fp32 [C,P]                      */
+int kws_fold_temporal_weights(const float* conv_w, const float* conv_b, const float* gamma, const float* beta,
+                              const float* mean, const float* var, float eps, int C, int P, float* w_folded,
+                              float* b_folded, void* stream);
+
+/* fp32 -> bf16 (projector Linear weights, src/efficient_kws/model.py:92-104) */
+int kws_cast_f32_to_bf16(const float* src, void* dst_bf16, size_t n, void* stream);
+
+/* ---- per batch of keywords or utterances --------------------------------- */
+
+/* L variant operand preparation: sparse layer selection + L2 normalisation +
+ * mask folding + fp16 cast.  Replaces the norm/clamp/divide of sim_matrix
+ * (model.py:214-216), the layer slice x[-n_layers:] (dataset.py:570-573) and
+ * the two mask multiplies (model.py:187-191).
+ *   x fp32 [B,Cin,T,D]; layer_idx HOST int32 [C] (indices into Cin)
+ *   mask fp32 [B,C,T] or NULL; out fp16 [C,B,T,D]                             */
+int kws_normalize_rows(const float* x, int B, int Cin, int T, int D, const int32_t* layer_idx, int C,
+                       const float* mask, float eps, void* out_f16, void* stream);
+
+/* LE/LEF input staging: layer selection + bf16 cast into layer-major rows.
+ *   x fp32 [B,Cin,T,D] -> out bf16 [C, B*T, D]                                */
+int kws_cast_rows_bf16(const float* x, int B, int Cin, int T, int D, const int32_t* layer_idx, int C,
+                       void* out_bf16, void* stream);
+
+/* Per-layer MLP projector[i] = Linear(D,H) -> ReLU -> Linear(H,P), H = D/2
+ * (model.py:92-104, applied :146-150), as two tcgen05 GEMMs with fused
+ * bias/ReLU and bias/normalise/mask epilogues.
+ *   x bf16 [C,R,D] (R = B*T rows per layer), w1 bf16 [C,H,D], b1 fp32 [C,H],
+ *   w2 bf16 [C,P,H], b2 fp32 [C,P], hidden bf16 workspace [C,R,H]
+ *   mask fp32 [B,C,T] or NULL (only used by KWS_MLP_OUT_NORM_F16)
+ *   out: see out_mode.  Requires D % 64 == 0, H % 64 == 0, P % 16 == 0, P <= 256 */
+int kws_mlp(const void* x_bf16, int C, int B, int T, int D, int H, int P, const void* w1_bf16, const float* b1,
+            const void* w2_bf16, const float* b2, void* hidden_bf16, const float* mask, float eps, int out_mode,
+            void* out, void* stream);
+
+/* LEF temporal projector (BN folded) + MaxPool1d(3,2,1) + L2 normalisation +
+ * mask folding (model.py:107-124, :152-166, :214-216, :187-191).
+ *   proj fp32 [C,B,T,P] -> out fp16 [C,B,T2,P], T2 = ceil(T/2)
+ *   mask fp32 [B,C,T2] (pooled resolution) or NULL                            */
+int kws_temporal(const float* proj, int C, int B, int T, int P, const float* w_folded, const float* b_folded,
+                 const float* mask, float eps, void* out_f16, void* stream);
+
+/* ---- per (keyword, utterance) pair ---------------------------------------- */
+
+/* Layer-wise cosine-similarity 'images' of all K x U pairs: batched
+ * tcgen05/TMEM GEMM fed by TMA (replaces torch.bmm + permute + stack + mask,
+ * model.py:174-191, :217).
+ *   kwd_n fp16 [C,K,Tk,Dk], utt_n fp16 [C,U,Tu,Dk] (prepared operands)
+ *   feat_f32 fp32 [K,U,C,Tk,Tu] or NULL   (== KWSOutput.features per utterance)
+ *   feat_f16 fp16 [K,U,C,Tk,pitch16] or NULL (stem input), pitch16 >= Tu
+ *   pair_mode KWS_PAIRS_ALL: every keyword against every utterance (K*U pairs);
+ *             KWS_PAIRS_DIAG: U == K, keyword k against utterance k only (the
+ *             training-style batch of model.py:171-173; outputs are [K,C,Tk,*])
+ *   Requires Dk % 64 == 0, Tk <= 256.                                          */
+int kws_sim(const void* kwd_n, const void* utt_n, int C, int K, int U, int Tk, int Tu, int Dk, int pair_mode,
+            float* feat_f32, void* feat_f16, int pitch16, void* stream);
+
+/* ResNet stem Conv2d(C,64,7,stride 2,pad 3,bias=False) + BatchNorm2d + ReLU as
+ * a tap-decomposed tcgen05 implicit GEMM (HF modeling_resnet.py:39-54 via
+ * src/efficient_kws/resnet.py:38,53).
+ *   feat_f16 fp16 [pairs,C,Tk,pitch16]; w_packed/bias from kws_pack_stem_weights
+ *   out: [pairs,64,Ho,Wo] fp32 or [pairs,Ho,Wo,64] bf16, Ho=ceil(Tk/2), Wo=ceil(Tu/2)
+ *   Requires C <= 16 (one 16-channel group per pass).                           */
+int kws_stem(const void* feat_f16, int pairs, int C, int Tk, int Tu, int pitch16, const void* w_packed,
+             const float* bias, int out_mode, void* out, void* stream);
+
+/* ---- scores ---------------------------------------------------------------- */
+
+/* Detection score softmax(logits)[:,1] * hotword_mask (model.py:783-795) and
+ * thresholded detections (score >= threshold) for n pairs.
+ *   logits fp32 [n,2]; hotword_mask fp32 [n] or NULL; scores fp32 [n];
+ *   detections uint8 [n] or NULL                                               */
+int kws_scores(const float* logits, const float* hotword_mask, size_t n, float threshold, float* scores,
+               uint8_t* detections, void* stream);
+
+/* Per-utterance top-k over the keyword axis with deterministic tie-break
+ * (lower global keyword index first); used for the local top-k of a keyword
+ * shard and for merging the all-gathered candidates (replaces torch.topk,
+ * model.py:523).
+ *   scores fp32 [n_cand, U] (candidate-major), ids int32 [n_cand, U] or NULL
+ *   (NULL: candidate c has global id id_offset + c)
+ *   out_scores fp32 [k, U], out_ids int32 [k, U]; k <= 1024                     */
+int kws_topk(const float* scores, const int32_t* ids, int n_cand, int U, int id_offset, int k, float* out_scores,
+             int32_t* out_ids, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KWS_B200_H_ */
