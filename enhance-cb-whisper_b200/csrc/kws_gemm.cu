@@ -47,6 +47,7 @@ struct GemmParams {
   const float* bias;  // [C, cols]
   const float* mask;  // EPI 1 normalised: [B, C, T] or null
   int out_mode;       // EPI 1: KWS_MLP_OUT_*
+  int hidden_bf16;    // EPI 0: hidden stored as bf16 (else saturating fp16)
   int T, Cn;          // EPI 1 mask indexing: row r -> (b = r / T, t = r % T); Cn = layers
   float eps;
   // SIM
@@ -213,8 +214,7 @@ kws_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       } else if (p.epi == EPI_BIAS_RELU_BF16) {
         const int col0 = w.nt * p.block_n;
         const float* bias = p.bias + (long long)w.c * p.cols + col0;
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) +
-                           ((long long)w.c * p.rows + row) * p.cols + col0;
+        uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + ((long long)w.c * p.rows + row) * p.cols + col0;
         for (int ch = 0; ch < n_chunks; ++ch) {
           tmem_ld16(t_row + ch * 16, v);
           tmem_ld_wait();
@@ -224,7 +224,7 @@ kws_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             for (int e = 0; e < 8; ++e) {
               const float a = fmaxf(__uint_as_float(v[2 * e]) + __ldg(bias + ch * 16 + 2 * e), 0.f);
               const float b = fmaxf(__uint_as_float(v[2 * e + 1]) + __ldg(bias + ch * 16 + 2 * e + 1), 0.f);
-              pk[e] = pack_bf162(a, b);
+              pk[e] = p.hidden_bf16 ? pack_bf162(a, b) : pack_half2_sat(a, b);
             }
             uint4* dst = reinterpret_cast<uint4*>(o + ch * 16);
             dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -347,10 +347,11 @@ using namespace kws;
 
 extern "C" {
 
-int kws_mlp(const void* x_bf16, int C, int B, int T, int D, int H, int P, const void* w1_bf16, const float* b1,
-            const void* w2_bf16, const float* b2, void* hidden_bf16, const float* mask, float eps, int out_mode,
-            void* out, void* stream) {
-  KWS_CHECK_ARG(x_bf16 && w1_bf16 && b1 && w2_bf16 && b2 && hidden_bf16 && out, "mlp: null pointer");
+int kws_mlp(const void* x16, int C, int B, int T, int D, int H, int P, int dtype16, const void* w1_16,
+            const float* b1, const void* w2_16, const float* b2, void* hidden16, const float* mask, float eps,
+            int out_mode, void* out, void* stream) {
+  KWS_CHECK_ARG(x16 && w1_16 && b1 && w2_16 && b2 && hidden16 && out, "mlp: null pointer");
+  KWS_CHECK_ARG(dtype16 == KWS_F16 || dtype16 == KWS_BF16, "mlp: bad dtype16 %d", dtype16);
   KWS_CHECK_ARG(C > 0 && B > 0 && T > 0, "mlp: non-positive dimension");
   KWS_CHECK_ARG(D % 64 == 0 && D >= 64, "mlp: D=%d must be a multiple of 64", D);
   KWS_CHECK_ARG(H % 64 == 0 && H >= 64, "mlp: H=%d must be a multiple of 64", H);
@@ -365,32 +366,33 @@ int kws_mlp(const void* x_bf16, int C, int B, int T, int D, int H, int P, const 
   {
     CUtensorMap ma, mb;
     const int bn = (H % 128 == 0) ? 128 : 64;
-    if (int e = operand_map(&ma, x_bf16, D, (int)R, C, BLOCK_M)) return e;
-    if (int e = operand_map(&mb, w1_bf16, D, H, C, bn)) return e;
+    if (int e = operand_map(&ma, x16, D, (int)R, C, BLOCK_M)) return e;
+    if (int e = operand_map(&mb, w1_16, D, H, C, bn)) return e;
     GemmParams p{};
     p.epi = EPI_BIAS_RELU_BF16;
     p.num_kblocks = D / BLOCK_K;
     p.block_n = bn;
-    p.idesc = make_idesc_f16(BLOCK_M, bn, 1);
+    p.idesc = make_idesc_f16(BLOCK_M, bn, (uint32_t)dtype16);
+    p.hidden_bf16 = dtype16 == KWS_BF16;
     p.m_tiles = m_tiles;
     p.n_tiles = H / bn;
     p.num_items = (long long)C * m_tiles * p.n_tiles;
     p.rows = (int)R;
     p.cols = H;
-    p.out = hidden_bf16;
+    p.out = hidden16;
     p.bias = b1;
     if (int e = launch_gemm(ma, mb, p, st)) return e;
   }
   // ---- GEMM 2: out = hidden W2^T + b2 (+ normalise * mask) ----
   {
     CUtensorMap ma, mb;
-    if (int e = operand_map(&ma, hidden_bf16, H, (int)R, C, BLOCK_M)) return e;
-    if (int e = operand_map(&mb, w2_bf16, H, P, C, P)) return e;
+    if (int e = operand_map(&ma, hidden16, H, (int)R, C, BLOCK_M)) return e;
+    if (int e = operand_map(&mb, w2_16, H, P, C, P)) return e;
     GemmParams p{};
     p.epi = EPI_BIAS_OUT;
     p.num_kblocks = H / BLOCK_K;
     p.block_n = P;
-    p.idesc = make_idesc_f16(BLOCK_M, P, 1);
+    p.idesc = make_idesc_f16(BLOCK_M, P, (uint32_t)dtype16);
     p.m_tiles = m_tiles;
     p.n_tiles = 1;
     p.num_items = (long long)C * m_tiles;

@@ -31,11 +31,11 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
 
 // ---------------------------------------------------------------------------
 // rows: x fp32 [B,Cin,T,D] -> out 16-bit [C, B, T, D]
-// NORMALIZE: out = fp16(x * mask / max(||x||, eps)); else out = bf16(x)
+// NORMALIZE: out = fp16(x * mask / max(||x||, eps)); else out = bf16(x) or saturating fp16(x)
 // ---------------------------------------------------------------------------
 constexpr int ROW_MAX_V4 = 16;  // D <= 2048
 
-template <bool NORMALIZE>
+template <bool NORMALIZE, bool BF16>
 __global__ void __launch_bounds__(256) rows_kernel(const float* __restrict__ x, int B, int Cin, int T, int D,
                                                    LayerIdx lidx, int C, const float* __restrict__ mask,
                                                    float eps, uint16_t* __restrict__ out) {
@@ -74,9 +74,12 @@ __global__ void __launch_bounds__(256) rows_kernel(const float* __restrict__ x, 
         if (NORMALIZE) {
           o.x = pack_half2(v[i].x * scale, v[i].y * scale);
           o.y = pack_half2(v[i].z * scale, v[i].w * scale);
-        } else {
+        } else if (BF16) {
           o.x = pack_bf162(v[i].x, v[i].y);
           o.y = pack_bf162(v[i].z, v[i].w);
+        } else {
+          o.x = pack_half2_sat(v[i].x, v[i].y);
+          o.y = pack_half2_sat(v[i].z, v[i].w);
         }
         dst[idx] = o;
       }
@@ -84,7 +87,7 @@ __global__ void __launch_bounds__(256) rows_kernel(const float* __restrict__ x, 
   }
 }
 
-static int launch_rows(bool normalize, const float* x, int B, int Cin, int T, int D, const int32_t* layer_idx,
+static int launch_rows(bool normalize, int dtype16, const float* x, int B, int Cin, int T, int D, const int32_t* layer_idx,
                        int C, const float* mask, float eps, void* out, cudaStream_t st) {
   KWS_CHECK_ARG(x && out && layer_idx, "rows: null pointer");
   KWS_CHECK_ARG(B > 0 && Cin > 0 && T > 0 && C > 0, "rows: non-positive dimension");
@@ -105,9 +108,11 @@ static int launch_rows(bool normalize, const float* x, int B, int Cin, int T, in
   const long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
   if (normalize)
-    rows_kernel<true><<<(int)blocks, wpb * 32, 0, st>>>(x, B, Cin, T, D, li, C, mask, eps, (uint16_t*)out);
+    rows_kernel<true, false><<<(int)blocks, wpb * 32, 0, st>>>(x, B, Cin, T, D, li, C, mask, eps, (uint16_t*)out);
+  else if (dtype16 == KWS_BF16)
+    rows_kernel<false, true><<<(int)blocks, wpb * 32, 0, st>>>(x, B, Cin, T, D, li, C, nullptr, eps, (uint16_t*)out);
   else
-    rows_kernel<false><<<(int)blocks, wpb * 32, 0, st>>>(x, B, Cin, T, D, li, C, nullptr, eps, (uint16_t*)out);
+    rows_kernel<false, false><<<(int)blocks, wpb * 32, 0, st>>>(x, B, Cin, T, D, li, C, nullptr, eps, (uint16_t*)out);
   KWS_CUDA(cudaGetLastError());
   return 0;
 }
@@ -231,9 +236,11 @@ __global__ void fold_temporal_kernel(const float* __restrict__ w, const float* _
   }
 }
 
-__global__ void cast_bf16_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, size_t n) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    d[i] = __float2bfloat16_rn(s[i]);
+__global__ void cast16_kernel(const float* __restrict__ s, uint16_t* __restrict__ d, size_t n, int bf16) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = s[i];
+    d[i] = (uint16_t)((bf16 ? pack_bf162(v, 0.f) : pack_half2_sat(v, 0.f)) & 0xffffu);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -308,12 +315,13 @@ extern "C" {
 
 int kws_normalize_rows(const float* x, int B, int Cin, int T, int D, const int32_t* layer_idx, int C,
                        const float* mask, float eps, void* out_f16, void* stream) {
-  return launch_rows(true, x, B, Cin, T, D, layer_idx, C, mask, eps, out_f16, (cudaStream_t)stream);
+  return launch_rows(true, KWS_F16, x, B, Cin, T, D, layer_idx, C, mask, eps, out_f16, (cudaStream_t)stream);
 }
 
-int kws_cast_rows_bf16(const float* x, int B, int Cin, int T, int D, const int32_t* layer_idx, int C,
-                       void* out_bf16, void* stream) {
-  return launch_rows(false, x, B, Cin, T, D, layer_idx, C, nullptr, 0.f, out_bf16, (cudaStream_t)stream);
+int kws_cast_rows16(const float* x, int B, int Cin, int T, int D, const int32_t* layer_idx, int C, int dtype16,
+                    void* out16, void* stream) {
+  KWS_CHECK_ARG(dtype16 == KWS_F16 || dtype16 == KWS_BF16, "cast_rows16: bad dtype16 %d", dtype16);
+  return launch_rows(false, dtype16, x, B, Cin, T, D, layer_idx, C, nullptr, 0.f, out16, (cudaStream_t)stream);
 }
 
 int kws_temporal(const float* proj, int C, int B, int T, int P, const float* w_folded, const float* b_folded,
@@ -359,12 +367,13 @@ int kws_fold_temporal_weights(const float* conv_w, const float* conv_b, const fl
   return 0;
 }
 
-int kws_cast_f32_to_bf16(const float* src, void* dst_bf16, size_t n, void* stream) {
-  KWS_CHECK_ARG(src && dst_bf16, "cast: null pointer");
+int kws_cast_f32_to_16(const float* src, void* dst16, size_t n, int dtype16, void* stream) {
+  KWS_CHECK_ARG(src && dst16, "cast: null pointer");
+  KWS_CHECK_ARG(dtype16 == KWS_F16 || dtype16 == KWS_BF16, "cast: bad dtype16 %d", dtype16);
   if (n == 0) return 0;
   size_t blocks = (n + 255) / 256;
   if (blocks > 4096) blocks = 4096;
-  cast_bf16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst_bf16, n);
+  cast16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(src, (uint16_t*)dst16, n, dtype16 == KWS_BF16);
   KWS_CUDA(cudaGetLastError());
   return 0;
 }

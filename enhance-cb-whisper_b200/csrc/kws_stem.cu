@@ -20,23 +20,27 @@
 // from global exactly once per column tile); weights (49 taps x 2 KB) stay
 // resident in shared memory for the life of the CTA.
 //
-// Roles (320 threads): warp 0 = TMEM allocator, warp 1 = MMA issuer,
-// warps 2..5 = loaders (global fp16 planar -> smem parity planes),
-// warps 6..9 = epilogue (TMEM -> +bias, ReLU -> global).
+// Roles (352 threads): warp 0 = TMEM allocator, warp 1 = MMA issuer,
+// warps 2..6 = loaders (global fp16 planar -> smem parity planes; one thread
+// per plane pixel, software-pipelined one row pair ahead),
+// warps 7..10 = epilogue (TMEM -> +bias, ReLU -> global).
 #include "kws_common.cuh"
 #include "../../include/kws_b200.h"
 
 namespace kws {
 
-constexpr int STEM_THREADS = 320;
+constexpr int STEM_THREADS = 352;
+constexpr int LOADER_THREADS = 160;        // warps 2..6; threads 0..131 own one plane pixel each
+constexpr int FIRST_EPI_WARP = 7;
 constexpr int OC = 64;
 constexpr int TILE_OJ = 128;               // output columns per tile (= UMMA M)
-constexpr int PLANE_JJ = 132;              // pixels per parity plane row (128 + 3 halo, padded)
+constexpr int PLANE_JJ = 132;              // pixels per parity plane row: x = j - (256 ct - 4), jj = x >> 1
+constexpr int X_ORIGIN = 4;                // tile column x = 0 is input column 256 ct - 4 (even: 32-bit loads)
 constexpr int CHUNK_BYTES = PLANE_JJ * 16;  // 2112: one 8-channel chunk of one plane row
 constexpr int PLANE_BYTES = 2 * CHUNK_BYTES;  // 4224: 16 channels
 constexpr int ROW_BYTES = 2 * PLANE_BYTES;    // 8448: both parities
 constexpr int SLOT_BYTES = 2 * ROW_BYTES;     // 16896: a pair of input rows
-constexpr int RING_SLOTS = 6;
+constexpr int RING_SLOTS = 7;
 constexpr int TAP_BYTES = 2 * OC * 16;  // 2048: [chunk][oc][8 ch] fp16
 constexpr int W_BYTES = 49 * TAP_BYTES;  // 100352
 constexpr int NUM_ACC = 4;
@@ -75,7 +79,7 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) kws_stem_kernel(const StemPar
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < RING_SLOTS; ++s) {
-      mbar_init(&full_bar[s], 128);
+      mbar_init(&full_bar[s], LOADER_THREADS);
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < NUM_ACC; ++a) {
@@ -97,8 +101,8 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) kws_stem_kernel(const StemPar
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16(TILE_OJ, OC, 0);
-      const uint32_t w_addr = smem_u32(s_w);
-      const uint32_t ring_addr = smem_u32(s_ring);
+      const uint64_t adesc0 = make_smem_desc(smem_u32(s_ring), CHUNK_BYTES, 128, LAYOUT_NONE);
+      const uint64_t bdesc0 = make_smem_desc(smem_u32(s_w), OC * 16, 128, LAYOUT_NONE);
       uint32_t pair_seq = 0;  // global sequence number of the first row pair of this item
       uint32_t row_seq = 0;   // global output-row counter -> accumulator buffer
       for (long long it = blockIdx.x; it < p.num_items; it += gridDim.x, pair_seq += NP) {
@@ -113,16 +117,17 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) kws_stem_kernel(const StemPar
           }
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * OC;
+          // descriptors differ from the two bases only in the 16-byte-granular start address
 #pragma unroll 1
           for (int di = 0; di < 7; ++di) {
             const uint32_t g = pair_seq + oi + (di >> 1);
-            const uint32_t row_addr = ring_addr + (g % RING_SLOTS) * SLOT_BYTES + (di & 1) * ROW_BYTES;
+            const uint64_t a_row = adesc0 + (uint64_t)(((g % RING_SLOTS) * SLOT_BYTES + (di & 1) * ROW_BYTES) >> 4);
+            const uint64_t b_row = bdesc0 + (uint64_t)((di * 7 * TAP_BYTES) >> 4);
 #pragma unroll
             for (int dj = 0; dj < 7; ++dj) {
-              const uint32_t a_addr = row_addr + (dj & 1) * PLANE_BYTES + (dj >> 1) * 16;
-              const uint64_t adesc = make_smem_desc(a_addr, CHUNK_BYTES, 128, LAYOUT_NONE);
-              const uint64_t bdesc = make_smem_desc(w_addr + (di * 7 + dj) * TAP_BYTES, OC * 16, 128, LAYOUT_NONE);
-              umma_f16(d_tmem, adesc, bdesc, idesc, (di | dj) != 0);
+              // input column 2 oj + dj - 3  ->  x = 2 ojl + dj + 1: plane (dj+1)&1, pixel ojl + ((dj+1)>>1)
+              umma_f16(d_tmem, a_row + (uint64_t)((((dj + 1) & 1) * PLANE_BYTES + ((dj + 1) >> 1) * 16) >> 4),
+                       b_row + (uint64_t)((dj * TAP_BYTES) >> 4), idesc, (di | dj) != 0);
             }
           }
           // row pair `oi` is dead once these MMAs retire; the accumulator is complete
@@ -140,49 +145,72 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) kws_stem_kernel(const StemPar
         }
       }
     }
-  } else if (warp >= 2 && warp < 6) {
+  } else if (warp >= 2 && warp < FIRST_EPI_WARP) {
     // ===================== loaders =====================
-    const int t = threadIdx.x - 64;  // 0..127
-    uint32_t g = 0;                   // global row-pair sequence number
-    for (long long it = blockIdx.x; it < p.num_items; it += gridDim.x) {
+    // Thread jj owns plane pixel jj of both parities: one 32-bit load fetches input columns
+    // (j, j+1) = (even x, odd x) of one channel; 16 channels x 2 rows = 32 loads in flight per
+    // thread, issued one row pair ahead of the stores (register double buffer).
+    const int jj = threadIdx.x - 64;  // 0..159, active < PLANE_JJ
+    const bool active = jj < PLANE_JJ;
+    const long long my_items = (p.num_items - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    const long long total = my_items * NP;  // row pairs this CTA streams
+    const long long ch_stride = (long long)p.Tk * p.pitch;
+
+    auto load_pair = [&](long long n, uint32_t (&v)[32]) {
+      const long long it = blockIdx.x + (n / NP) * gridDim.x;
+      const int s = (int)(n % NP);
       const long long pair = it / p.col_tiles;
       const int ct = (int)(it % p.col_tiles);
-      const int j_base = ct * (2 * TILE_OJ) - 3;  // input column of plane position x = 0
-      const __half* f_pair = p.feat + pair * (long long)p.C * p.Tk * p.pitch;
-      for (int s = 0; s < NP; ++s, ++g) {
-        const uint32_t slot = g % RING_SLOTS;
-        mbar_wait(&empty_bar[slot], ((g / RING_SLOTS) & 1) ^ 1, 100 + (int)slot);
-        uint8_t* s_slot = s_ring + slot * SLOT_BYTES;
-#pragma unroll 1
-        for (int pos = t; pos < 2 * PLANE_JJ; pos += 128) {
-          const int pj = pos >= PLANE_JJ ? 1 : 0;
-          const int jj = pos - pj * PLANE_JJ;
-          const int j = j_base + 2 * jj + pj;
-          const bool col_ok = (j >= 0) && (j < p.Tu);
+      const int j = ct * (2 * TILE_OJ) - X_ORIGIN + 2 * jj;  // even
+      const bool lo_ok = active && j >= 0 && j < p.Tu;
+      const uint32_t keep = (j + 1 < p.Tu) ? 0xffffffffu : 0x0000ffffu;
+      const __half* f_pair = p.feat + pair * (long long)p.C * ch_stride + j;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int r = 2 * s + h - 3;
-            const bool ok = col_ok && (r >= 0) && (r < p.Tk);
-            uint32_t pk[8];
+      for (int h = 0; h < 2; ++h) {
+        const int r = 2 * s + h - 3;
+        const bool ok = lo_ok && r >= 0 && r < p.Tk;
+        const __half* f_row = f_pair + (long long)r * p.pitch;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              unsigned short lo = 0, hi = 0;
-              if (ok && 2 * e < p.C)
-                lo = __ldg(reinterpret_cast<const unsigned short*>(f_pair + ((long long)(2 * e) * p.Tk + r) * p.pitch + j));
-              if (ok && 2 * e + 1 < p.C)
-                hi = __ldg(reinterpret_cast<const unsigned short*>(f_pair + ((long long)(2 * e + 1) * p.Tk + r) * p.pitch + j));
-              pk[e] = (uint32_t)lo | ((uint32_t)hi << 16);
-            }
-            uint8_t* dst = s_slot + h * ROW_BYTES + pj * PLANE_BYTES + jj * 16;
-            *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            *reinterpret_cast<uint4*>(dst + CHUNK_BYTES) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        for (int c = 0; c < 16; ++c) {
+          uint32_t x = 0;
+          if (ok && c < p.C) x = __ldg(reinterpret_cast<const unsigned int*>(f_row + c * ch_stride)) & keep;
+          v[h * 16 + c] = x;
+        }
+      }
+    };
+    auto store_pair = [&](long long n, const uint32_t (&v)[32]) {
+      const uint32_t slot = (uint32_t)(n % RING_SLOTS);
+      mbar_wait(&empty_bar[slot], (uint32_t)((n / RING_SLOTS) & 1) ^ 1, 100 + (int)slot);
+      if (active) {
+        uint8_t* dst = s_ring + slot * SLOT_BYTES + jj * 16;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {  // 8-channel chunk
+            const uint32_t* q = &v[h * 16 + k * 8];
+            // plane 0 <- low halves (even x), plane 1 <- high halves (odd x)
+            *reinterpret_cast<uint4*>(dst + h * ROW_BYTES + k * CHUNK_BYTES) =
+                make_uint4(__byte_perm(q[0], q[1], 0x5410), __byte_perm(q[2], q[3], 0x5410),
+                           __byte_perm(q[4], q[5], 0x5410), __byte_perm(q[6], q[7], 0x5410));
+            *reinterpret_cast<uint4*>(dst + h * ROW_BYTES + PLANE_BYTES + k * CHUNK_BYTES) =
+                make_uint4(__byte_perm(q[0], q[1], 0x7632), __byte_perm(q[2], q[3], 0x7632),
+                           __byte_perm(q[4], q[5], 0x7632), __byte_perm(q[6], q[7], 0x7632));
           }
         }
-        fence_proxy_async();
-        mbar_arrive(&full_bar[slot]);
       }
+      fence_proxy_async();
+      mbar_arrive(&full_bar[slot]);
+    };
+
+    uint32_t va[32], vb[32];
+    if (total > 0) load_pair(0, va);
+    for (long long n = 0; n < total; n += 2) {
+      if (n + 1 < total) load_pair(n + 1, vb);
+      store_pair(n, va);
+      if (n + 2 < total) load_pair(n + 2, va);
+      if (n + 1 < total) store_pair(n + 1, vb);
     }
-  } else if (warp >= 6) {
+  } else if (warp >= FIRST_EPI_WARP) {
     // ===================== epilogue =====================
     const int q = warp & 3;
     const int ojl = q * 32 + lane;

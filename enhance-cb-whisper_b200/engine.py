@@ -28,9 +28,10 @@ class PackedWeights:
     C: int
     D: int
     P: int
-    w1: Optional[torch.Tensor] = None  # bf16 [C,H,D]
+    mlp_dtype16: int = ops.F16  # operand type of the projector GEMMs (ops.F16 | ops.BF16)
+    w1: Optional[torch.Tensor] = None  # 16-bit [C,H,D]
     b1: Optional[torch.Tensor] = None  # fp32 [C,H]
-    w2: Optional[torch.Tensor] = None  # bf16 [C,P,H]
+    w2: Optional[torch.Tensor] = None  # 16-bit [C,P,H]
     b2: Optional[torch.Tensor] = None  # fp32 [C,P]
     wt: Optional[torch.Tensor] = None  # fp32 [C,3,P,P]  temporal conv, BN folded
     bt: Optional[torch.Tensor] = None  # fp32 [C,P]
@@ -43,17 +44,22 @@ class PackedWeights:
 
 
 def pack_weights(sd: Mapping[str, torch.Tensor], variant: str, C: int, D: int, P: int,
-                 device: torch.device) -> PackedWeights:
+                 device: torch.device, mlp_dtype16: int = ops.F16) -> PackedWeights:
     """Pack a reference-keyed state_dict (projector.{i}.{0,2}.*, time_projector.{i}.{0,1}.*,
-    model.feature_extractor.embedder.embedder.*) for the kernels."""
+    model.feature_extractor.embedder.embedder.*) for the kernels.
+
+    ``mlp_dtype16``: fp16 (default) keeps the similarity of the LE/LEF variants within the 2e-3
+    parity bound -- the reference's inputs are L2-normalised (src/utils.py:195) so |x| <= 1 and
+    |hidden| <= ||W1_j|| + |b1_j|, far inside fp16 range; conversions saturate instead of
+    overflowing.  bf16 is range-safe for arbitrary activations at ~3e-3 similarity error."""
     def dev(k):
         return sd[k].detach().to(device=device, dtype=torch.float32)
 
-    pw = PackedWeights(variant=variant, C=C, D=D, P=P)
+    pw = PackedWeights(variant=variant, C=C, D=D, P=P, mlp_dtype16=mlp_dtype16)
     if variant in ("LE", "LEF"):
-        pw.w1 = ops.cast_bf16(torch.stack([dev(f"projector.{i}.0.weight") for i in range(C)]))
+        pw.w1 = ops.cast16(torch.stack([dev(f"projector.{i}.0.weight") for i in range(C)]), mlp_dtype16)
         pw.b1 = torch.stack([dev(f"projector.{i}.0.bias") for i in range(C)]).contiguous()
-        pw.w2 = ops.cast_bf16(torch.stack([dev(f"projector.{i}.2.weight") for i in range(C)]))
+        pw.w2 = ops.cast16(torch.stack([dev(f"projector.{i}.2.weight") for i in range(C)]), mlp_dtype16)
         pw.b2 = torch.stack([dev(f"projector.{i}.2.bias") for i in range(C)]).contiguous()
     if variant == "LEF":
         st = lambda name: torch.stack([dev(f"time_projector.{i}.{name}") for i in range(C)])
@@ -104,7 +110,7 @@ class KWSEngine:
         step = max(1, min(B, self.workspace_bytes // max(per_item, 1)))
         for b0 in range(0, B, step):
             b1 = min(B, b0 + step)
-            xb = ops.cast_rows_bf16(x[b0:b1], layer_idx)
+            xb = ops.cast_rows16(x[b0:b1], layer_idx, w.mlp_dtype16)
             mb = mask[b0:b1].contiguous() if mask is not None else None
             if w.variant == "LE":
                 o = ops.mlp(xb, b1 - b0, T, w.w1, w.b1, w.w2, w.b2, mb, ops.MLP_OUT_NORM_F16)

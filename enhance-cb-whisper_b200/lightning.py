@@ -11,7 +11,8 @@ Switch one line of any ``src/efficient_kws/configs/*.yaml``::
 the unchanged ``init_args``; ``test_step`` / ``validation_step`` and every
 metric hook are inherited from the reference, only ``forward`` is replaced.
 Optional extra init args: ``b200_body_dtype`` ("float32" | "bfloat16"),
-``b200_return_features`` (bool), ``b200_layer_idx`` (list of int).
+``b200_return_features`` (bool), ``b200_layer_idx`` (list of int), ``b200_mlp_dtype``
+("float16" | "bfloat16").
 """
 from __future__ import annotations
 
@@ -29,9 +30,10 @@ from .model import B200ForwardMixin
 
 class KWSModelB200(B200ForwardMixin, _ReferenceKWSModel):
     def __init__(self, *args, b200_body_dtype: str = "float32", b200_return_features: bool = True,
-                 b200_layer_idx=None, **kwargs):
+                 b200_layer_idx=None, b200_mlp_dtype: str = "float16", **kwargs):
         super().__init__(*args, **kwargs)
         self.b200_body_dtype = b200_body_dtype
         self.b200_return_features = b200_return_features
         self.b200_layer_idx = b200_layer_idx
+        self.b200_mlp_dtype = b200_mlp_dtype
         self._b200_init()

@@ -101,6 +101,7 @@ class B200ForwardMixin:
     b200_body_dtype: str = "float32"  # "float32" (parity) | "bfloat16" (throughput, channels_last)
     b200_return_features: bool = True  # materialise KWSOutput.features (fp32) like the reference
     b200_layer_idx: Optional[Sequence[int]] = None  # explicit layer selection into the given stack
+    b200_mlp_dtype: str = "float16"  # projector GEMM operands: "float16" (parity) | "bfloat16" (range-safe)
 
     def _b200_init(self):
         self._packed: Optional[PackedWeights] = None
@@ -132,7 +133,8 @@ class B200ForwardMixin:
         if self._engine is None or self._packed_key != key:
             hp = self.hparams
             sd = {k: v for k, v in self.state_dict().items()}
-            self._packed = pack_weights(sd, self.variant, hp.n_layers, hp.embedding_dim, hp.proj_mlp_units, device)
+            self._packed = pack_weights(sd, self.variant, hp.n_layers, hp.embedding_dim, hp.proj_mlp_units, device,
+                                        ops.F16 if self.b200_mlp_dtype == "float16" else ops.BF16)
             self._engine = KWSEngine(self._packed)
             self._packed_key = key
             self._body_lowp = None

@@ -12,8 +12,10 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import (MLP_OUT_NORM_F16, MLP_OUT_RAW_F32, PAIRS_ALL, PAIRS_DIAG, STEM_OUT_NCHW_F32,
-                   STEM_OUT_NHWC_BF16, KWSError, check)
+from ._lib import (BF16, F16, MLP_OUT_NORM_F16, MLP_OUT_RAW_F32, PAIRS_ALL, PAIRS_DIAG, STEM_OUT_NCHW_F32,
+                   STEM_OUT_NHWC_BF16, KWSError)
+
+TORCH16 = {F16: torch.float16, BF16: torch.bfloat16}
 
 SIM_EPS = 1e-6  # reference src/efficient_kws/model.py:210
 BN_EPS = 1e-5
@@ -33,6 +35,17 @@ def _cuda(t: Optional[torch.Tensor], name: str, dtype=None) -> int:
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+# kernels launched through this module since import (bench.py reports the count of the timed region)
+LAUNCHES = 0
+_KERNELS_PER_CALL = {"kws_mlp": 2}
+
+
+def check(rc: int, what: str) -> None:  # noqa: F811 - wraps _lib.check with launch accounting
+    global LAUNCHES
+    _lib.check(rc, what)
+    LAUNCHES += _KERNELS_PER_CALL.get(what, 1)
 
 
 def _layers(layer_idx: Sequence[int]):
@@ -72,12 +85,13 @@ def fold_temporal_weights(conv_w, conv_b, gamma, beta, mean, var, eps: float = B
     return wf, bf
 
 
-def cast_bf16(src: torch.Tensor) -> torch.Tensor:
+def cast16(src: torch.Tensor, dtype16: int = F16) -> torch.Tensor:
+    """fp32 -> fp16 (saturating) | bf16"""
     lib = _lib.load()
     src = src.detach().float().contiguous()
-    dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
-    check(lib.kws_cast_f32_to_bf16(_cuda(src, "src", torch.float32), _cuda(dst, "dst"), src.numel(), _stream()),
-          "kws_cast_f32_to_bf16")
+    dst = torch.empty(src.shape, dtype=TORCH16[dtype16], device=src.device)
+    check(lib.kws_cast_f32_to_16(_cuda(src, "src", torch.float32), _cuda(dst, "dst"), src.numel(), dtype16,
+                                 _stream()), "kws_cast_f32_to_16")
     return dst
 
 
@@ -97,33 +111,38 @@ def normalize_rows(x: torch.Tensor, layer_idx: Sequence[int], mask: Optional[tor
     return out
 
 
-def cast_rows_bf16(x: torch.Tensor, layer_idx: Sequence[int]) -> torch.Tensor:
-    """x fp32 [B,Cin,T,D] -> bf16 [C, B*T, D]."""
+def cast_rows16(x: torch.Tensor, layer_idx: Sequence[int], dtype16: int = F16) -> torch.Tensor:
+    """x fp32 [B,Cin,T,D] -> fp16|bf16 [C, B*T, D] (selected layers, layer-major rows)."""
     lib = _lib.load()
     B, Cin, T, D = x.shape
     Cc = len(layer_idx)
-    out = torch.empty((Cc, B * T, D), dtype=torch.bfloat16, device=x.device)
-    check(lib.kws_cast_rows_bf16(_cuda(x, "x", torch.float32), B, Cin, T, D, _layers(layer_idx), Cc,
-                                 _cuda(out, "out"), _stream()), "kws_cast_rows_bf16")
+    out = torch.empty((Cc, B * T, D), dtype=TORCH16[dtype16], device=x.device)
+    check(lib.kws_cast_rows16(_cuda(x, "x", torch.float32), B, Cin, T, D, _layers(layer_idx), Cc, dtype16,
+                              _cuda(out, "out"), _stream()), "kws_cast_rows16")
     return out
 
 
-def mlp(x_bf16: torch.Tensor, B: int, T: int, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor,
+def mlp(x16: torch.Tensor, B: int, T: int, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor,
         b2: torch.Tensor, mask: Optional[torch.Tensor], out_mode: int, eps: float = SIM_EPS) -> torch.Tensor:
-    """x bf16 [C,B*T,D]; w1 bf16 [C,H,D]; b1 fp32 [C,H]; w2 bf16 [C,P,H]; b2 fp32 [C,P]
+    """x [C,B*T,D]; w1 [C,H,D]; w2 [C,P,H] all fp16 or all bf16; b1 fp32 [C,H]; b2 fp32 [C,P]
     -> fp16 [C,B,T,P] (normalised) or fp32 [C,B,T,P] (raw)."""
     lib = _lib.load()
+    x_bf16 = x16
+    dt = x16.dtype
+    if dt not in (torch.float16, torch.bfloat16) or w1.dtype != dt or w2.dtype != dt:
+        raise KWSError(f"x/w1/w2 must share one 16-bit dtype, got {x16.dtype}/{w1.dtype}/{w2.dtype}")
+    dtype16 = F16 if dt == torch.float16 else BF16
     Cc, R, D = x_bf16.shape
     H, P = w1.shape[1], w2.shape[1]
     if R != B * T:
         raise KWSError(f"x rows {R} != B*T = {B * T}")
     if tuple(w1.shape) != (Cc, H, D) or tuple(w2.shape) != (Cc, P, H):
         raise KWSError("projector weight shapes do not match x")
-    hidden = torch.empty((Cc, R, H), dtype=torch.bfloat16, device=x_bf16.device)
+    hidden = torch.empty((Cc, R, H), dtype=dt, device=x_bf16.device)
     out = torch.empty((Cc, B, T, P), dtype=torch.float16 if out_mode == MLP_OUT_NORM_F16 else torch.float32,
                       device=x_bf16.device)
-    check(lib.kws_mlp(_cuda(x_bf16, "x", torch.bfloat16), Cc, B, T, D, H, P, _cuda(w1, "w1", torch.bfloat16),
-                      _cuda(b1, "b1", torch.float32), _cuda(w2, "w2", torch.bfloat16),
+    check(lib.kws_mlp(_cuda(x_bf16, "x", dt), Cc, B, T, D, H, P, dtype16, _cuda(w1, "w1", dt),
+                      _cuda(b1, "b1", torch.float32), _cuda(w2, "w2", dt),
                       _cuda(b2, "b2", torch.float32), _cuda(hidden, "hidden"),
                       _cuda(mask, "mask", torch.float32), eps, out_mode, _cuda(out, "out"), _stream()), "kws_mlp")
     return out

@@ -36,6 +36,10 @@ extern "C" {
 
 #define KWS_ABI_VERSION 1
 
+/* 16-bit operand formats (same encoding as the tcgen05 kind::f16 descriptor) */
+#define KWS_F16 0  /* IEEE half: 10-bit mantissa; for L2-normalised data and sane weights */
+#define KWS_BF16 1 /* bfloat16: 7-bit mantissa, fp32 range                               */
+
 /* kws_mlp out_mode */
 #define KWS_MLP_OUT_NORM_F16 0 /* LE : fp16 [C,R,P], row-normalised * mask          */
 #define KWS_MLP_OUT_RAW_F32 1  /* LEF: fp32 [C,R,P], un-normalised (feeds kws_temporal) */
@@ -76,8 +80,8 @@ int kws_fold_temporal_weights(const float* conv_w, const float* conv_b, const fl
                               const float* mean, const float* var, float eps, int C, int P, float* w_folded,
                               float* b_folded, void* stream);
 
-/* fp32 -> bf16 (projector Linear weights, src/efficient_kws/model.py:92-104) */
-int kws_cast_f32_to_bf16(const float* src, void* dst_bf16, size_t n, void* stream);
+/* fp32 -> fp16/bf16, saturating (projector Linear weights, src/efficient_kws/model.py:92-104) */
+int kws_cast_f32_to_16(const float* src, void* dst16, size_t n, int dtype16, void* stream);
 
 /* ---- per batch of keywords or utterances --------------------------------- */
 
@@ -90,21 +94,21 @@ int kws_cast_f32_to_bf16(const float* src, void* dst_bf16, size_t n, void* strea
 int kws_normalize_rows(const float* x, int B, int Cin, int T, int D, const int32_t* layer_idx, int C,
                        const float* mask, float eps, void* out_f16, void* stream);
 
-/* LE/LEF input staging: layer selection + bf16 cast into layer-major rows.
- *   x fp32 [B,Cin,T,D] -> out bf16 [C, B*T, D]                                */
-int kws_cast_rows_bf16(const float* x, int B, int Cin, int T, int D, const int32_t* layer_idx, int C,
-                       void* out_bf16, void* stream);
+/* LE/LEF input staging: layer selection + 16-bit cast into layer-major rows.
+ *   x fp32 [B,Cin,T,D] -> out fp16|bf16 [C, B*T, D]                            */
+int kws_cast_rows16(const float* x, int B, int Cin, int T, int D, const int32_t* layer_idx, int C, int dtype16,
+                    void* out16, void* stream);
 
 /* Per-layer MLP projector[i] = Linear(D,H) -> ReLU -> Linear(H,P), H = D/2
  * (model.py:92-104, applied :146-150), as two tcgen05 GEMMs with fused
  * bias/ReLU and bias/normalise/mask epilogues.
- *   x bf16 [C,R,D] (R = B*T rows per layer), w1 bf16 [C,H,D], b1 fp32 [C,H],
- *   w2 bf16 [C,P,H], b2 fp32 [C,P], hidden bf16 workspace [C,R,H]
+ *   x [C,R,D] (R = B*T rows per layer), w1 [C,H,D], w2 [C,P,H], hidden workspace [C,R,H]: all of
+ *   the 16-bit type dtype16 (KWS_F16 | KWS_BF16); b1 fp32 [C,H], b2 fp32 [C,P]
  *   mask fp32 [B,C,T] or NULL (only used by KWS_MLP_OUT_NORM_F16)
  *   out: see out_mode.  Requires D % 64 == 0, H % 64 == 0, P % 16 == 0, P <= 256 */
-int kws_mlp(const void* x_bf16, int C, int B, int T, int D, int H, int P, const void* w1_bf16, const float* b1,
-            const void* w2_bf16, const float* b2, void* hidden_bf16, const float* mask, float eps, int out_mode,
-            void* out, void* stream);
+int kws_mlp(const void* x16, int C, int B, int T, int D, int H, int P, int dtype16, const void* w1_16,
+            const float* b1, const void* w2_16, const float* b2, void* hidden16, const float* mask, float eps,
+            int out_mode, void* out, void* stream);
 
 /* LEF temporal projector (BN folded) + MaxPool1d(3,2,1) + L2 normalisation +
  * mask folding (model.py:107-124, :152-166, :214-216, :187-191).

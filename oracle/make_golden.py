@@ -62,6 +62,22 @@ def build_body(C: int, resnet_version: str, body_seed: int):
     return fe.eval(), head.eval()
 
 
+def assemble_body(meta, sd):
+    """Rebuild the seeded body for a fixture and load the fixture's stem weights into it.
+    Returns (feature_extractor, head, same) where ``same`` says whether the regenerated
+    weights reproduce the checksum recorded when the fixture was made."""
+    fe, head = build_body(meta["C"], meta["resnet_version"], meta["body_seed"])
+    stem_sd = {k[len("model.feature_extractor."):]: v for k, v in sd.items() if k.startswith("model.feature_extractor.")}
+    fe.load_state_dict(stem_sd, strict=False)
+    tot = 0.0
+    for mod in (fe, head):
+        for v in mod.state_dict().values():
+            if v.is_floating_point():
+                tot += float(v.double().abs().sum())
+    same = abs(tot - meta["body_checksum"]) <= 1e-9 * max(1.0, abs(meta["body_checksum"]))
+    return fe, head, same
+
+
 def make_case(name: str, body_seed: int = 7):
     variant, K, U, C, D, P, Tk, Tu, rv, ghost = CASES[name]
     if variant == "L":

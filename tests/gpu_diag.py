@@ -72,8 +72,10 @@ def test_prep(gen):
     xs = x[:, lidx].permute(1, 0, 2, 3)
     exp = xs / xs.norm(dim=-1, keepdim=True).clamp(min=1e-6) * mask.permute(1, 0, 2)[..., None]
     report("normalize_rows", out, exp, 1e-3)
-    ob = ops.cast_rows_bf16(x, lidx)
-    report("cast_rows_bf16", ob.view(3, B, T, D), xs.bfloat16(), 0.0)
+    ob = ops.cast_rows16(x, lidx, ops.BF16)
+    report("cast_rows16 bf16", ob.view(3, B, T, D), xs.bfloat16(), 0.0)
+    oh = ops.cast_rows16(x, lidx, ops.F16)
+    report("cast_rows16 f16", oh.view(3, B, T, D), xs.half(), 0.0)
 
 
 def gemm_probe(Dk, Tk, Tu):
@@ -112,22 +114,24 @@ def test_sim(gen, shapes):
 
 def test_mlp(gen):
     print("== MLP (two tcgen05 GEMMs) ==")
-    for (Cc, B, T, D, P) in [(2, 3, 50, 128, 64), (3, 2, 150, 768, 64), (1, 1, 300, 256, 32)]:
+    for (Cc, B, T, D, P, d16) in [(2, 3, 50, 128, 64, ops.BF16), (3, 2, 150, 768, 64, ops.F16),
+                                  (1, 1, 300, 256, 32, ops.F16)]:
         H = D // 2
+        tdt = ops.TORCH16[d16]
         x = unit_rows(B, Cc, T, D, gen=gen)
         w1 = torch.randn(Cc, H, D, generator=gen, device=dev) * (4.0 / D ** 0.5)
         b1 = torch.randn(Cc, H, generator=gen, device=dev) * 0.05
         w2 = torch.randn(Cc, P, H, generator=gen, device=dev) / H ** 0.5
         b2 = torch.randn(Cc, P, generator=gen, device=dev) * 0.05
         mask = (torch.rand(B, Cc, T, generator=gen, device=dev) > 0.1).float()
-        xb = ops.cast_rows_bf16(x, list(range(Cc)))
-        w1b, w2b = ops.cast_bf16(w1), ops.cast_bf16(w2)
+        xb = ops.cast_rows16(x, list(range(Cc)), d16)
+        w1b, w2b = ops.cast16(w1, d16), ops.cast16(w2, d16)
         raw = ops.mlp(xb, B, T, w1b, b1, w2b, b2, None, ops.MLP_OUT_RAW_F32)
         # same-quantisation expectation: bf16 x, bf16 W1, fp32 acc, bf16 hidden, bf16 W2
         xq = xb.float().view(Cc, B, T, D)
-        h = torch.relu(torch.einsum("cbtd,chd->cbth", xq, w1b.float()) + b1[:, None, None, :]).bfloat16().float()
+        h = torch.relu(torch.einsum("cbtd,chd->cbth", xq, w1b.float()) + b1[:, None, None, :]).to(tdt).float()
         exp = torch.einsum("cbth,cph->cbtp", h, w2b.float()) + b2[:, None, None, :]
-        ok = report(f"mlp raw C{Cc} B{B} T{T} D{D} P{P}", raw, exp, 2e-3)
+        ok = report(f"mlp raw C{Cc} B{B} T{T} D{D} P{P} {tdt}", raw, exp, 2e-3)
         nrm = ops.mlp(xb, B, T, w1b, b1, w2b, b2, mask, ops.MLP_OUT_NORM_F16)
         expn = exp / exp.norm(dim=-1, keepdim=True).clamp(min=1e-6) * mask.permute(1, 0, 2)[..., None]
         report("mlp norm", nrm, expn, 2e-3)
