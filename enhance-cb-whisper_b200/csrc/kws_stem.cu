@@ -55,6 +55,11 @@ struct StemParams {
   long long pairs;
   int C, Tk, Tu, pitch, Ho, Wo, col_tiles;
   long long num_items;
+  // channel groups (C > 16): one launch per 16-channel group, partial sums chained through an fp32
+  // [pairs,Ho,Wo,64] workspace; bias + ReLU + the final store happen in the last group's launch
+  int ch0;             // first input channel of this launch's group
+  const float* acc_in;  // partial sums of the previous groups (null for the first group)
+  float* acc_out;       // where to leave partial sums (null for the last group: write `out`)
 };
 
 __global__ void __launch_bounds__(STEM_THREADS, 1) kws_stem_kernel(const StemParams p) {
@@ -164,7 +169,7 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) kws_stem_kernel(const StemPar
       const int j = ct * (2 * TILE_OJ) - X_ORIGIN + 2 * jj;  // even
       const bool lo_ok = active && j >= 0 && j < p.Tu;
       const uint32_t keep = (j + 1 < p.Tu) ? 0xffffffffu : 0x0000ffffu;
-      const __half* f_pair = p.feat + pair * (long long)p.C * ch_stride + j;
+      const __half* f_pair = p.feat + (pair * (long long)p.C + p.ch0) * ch_stride + j;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int r = 2 * s + h - 3;
@@ -173,7 +178,7 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) kws_stem_kernel(const StemPar
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
           uint32_t x = 0;
-          if (ok && c < p.C) x = __ldg(reinterpret_cast<const unsigned int*>(f_row + c * ch_stride)) & keep;
+          if (ok && c + p.ch0 < p.C) x = __ldg(reinterpret_cast<const unsigned int*>(f_row + c * ch_stride)) & keep;
           v[h * 16 + c] = x;
         }
       }
@@ -235,7 +240,31 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) kws_stem_kernel(const StemPar
         // accumulator is in registers: hand the TMEM buffer back before the stores
         tc_fence_before();
         mbar_arrive(&aempty_bar[acc]);
-        if (ok) {
+        if (ok && (p.acc_in || p.acc_out)) {
+          const long long px = ((pair * p.Ho + oi) * (long long)p.Wo + oj) * OC;
+          if (p.acc_in) {
+            const float4* a = reinterpret_cast<const float4*>(p.acc_in + px);
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float4 f = a[ch * 4 + e];
+                v[ch][4 * e] = __float_as_uint(__uint_as_float(v[ch][4 * e]) + f.x);
+                v[ch][4 * e + 1] = __float_as_uint(__uint_as_float(v[ch][4 * e + 1]) + f.y);
+                v[ch][4 * e + 2] = __float_as_uint(__uint_as_float(v[ch][4 * e + 2]) + f.z);
+                v[ch][4 * e + 3] = __float_as_uint(__uint_as_float(v[ch][4 * e + 3]) + f.w);
+              }
+          }
+          if (p.acc_out) {
+            uint4* a = reinterpret_cast<uint4*>(p.acc_out + px);
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                a[ch * 4 + e] = make_uint4(v[ch][4 * e], v[ch][4 * e + 1], v[ch][4 * e + 2], v[ch][4 * e + 3]);
+          }
+        }
+        if (ok && !p.acc_out) {
           if (p.out_mode == KWS_STEM_OUT_NCHW_F32) {
             float* o = reinterpret_cast<float*>(p.out) + ((pair * OC) * p.Ho + oi) * (long long)p.Wo + oj;
             const long long oc_stride = (long long)p.Ho * p.Wo;
@@ -279,11 +308,18 @@ constexpr size_t STEM_SMEM = 1024 + W_BYTES + RING_SLOTS * SLOT_BYTES + (2 * RIN
 
 using namespace kws;
 
+extern "C" size_t kws_stem_workspace_bytes(int pairs, int C, int Tk, int Tu) {
+  if (C <= 16 || pairs <= 0 || Tk <= 0 || Tu <= 0) return 0;
+  return (size_t)pairs * ((Tk + 1) / 2) * ((Tu + 1) / 2) * OC * sizeof(float);
+}
+
 extern "C" int kws_stem(const void* feat_f16, int pairs, int C, int Tk, int Tu, int pitch16, const void* w_packed,
-                        const float* bias, int out_mode, void* out, void* stream) {
+                        const float* bias, int out_mode, void* out, void* workspace, void* stream) {
   KWS_CHECK_ARG(feat_f16 && w_packed && bias && out, "stem: null pointer");
   KWS_CHECK_ARG(pairs > 0 && Tk > 0 && Tu > 0, "stem: non-positive dimension");
-  KWS_CHECK_ARG(C > 0 && C <= 16, "stem: C=%d input channels; only C <= 16 is supported by this build", C);
+  KWS_CHECK_ARG(C > 0 && C <= 64, "stem: C=%d input channels out of (0,64]", C);
+  KWS_CHECK_ARG(C <= 16 || workspace, "stem: C=%d > 16 needs a workspace of kws_stem_workspace_bytes()", C);
+  KWS_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "stem: workspace must be 16-byte aligned");
   KWS_CHECK_ARG(pitch16 >= Tu, "stem: pitch16=%d < Tu=%d", pitch16, Tu);
   KWS_CHECK_ARG(out_mode == KWS_STEM_OUT_NCHW_F32 || out_mode == KWS_STEM_OUT_NHWC_BF16, "stem: bad out_mode %d",
                 out_mode);
@@ -305,7 +341,14 @@ extern "C" int kws_stem(const void* feat_f16, int pairs, int C, int Tk, int Tu, 
   long long grid = p.num_items;
   const int sms = sm_count();
   if (grid > sms) grid = sms;
-  kws_stem_kernel<<<(int)grid, STEM_THREADS, STEM_SMEM, (cudaStream_t)stream>>>(p);
-  KWS_CUDA(cudaGetLastError());
+  const int groups = (C + 15) / 16;
+  for (int g = 0; g < groups; ++g) {
+    p.ch0 = g * 16;
+    p.w = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(w_packed) + (size_t)g * W_BYTES);
+    p.acc_in = g > 0 ? reinterpret_cast<const float*>(workspace) : nullptr;
+    p.acc_out = g + 1 < groups ? reinterpret_cast<float*>(workspace) : nullptr;
+    kws_stem_kernel<<<(int)grid, STEM_THREADS, STEM_SMEM, (cudaStream_t)stream>>>(p);
+    KWS_CUDA(cudaGetLastError());
+  }
   return 0;
 }

@@ -42,10 +42,10 @@ LAUNCHES = 0
 _KERNELS_PER_CALL = {"kws_mlp": 2}
 
 
-def check(rc: int, what: str) -> None:  # noqa: F811 - wraps _lib.check with launch accounting
+def check(rc: int, what: str, launches: Optional[int] = None) -> None:  # _lib.check + launch accounting
     global LAUNCHES
     _lib.check(rc, what)
-    LAUNCHES += _KERNELS_PER_CALL.get(what, 1)
+    LAUNCHES += _KERNELS_PER_CALL.get(what, 1) if launches is None else launches
 
 
 def _layers(layer_idx: Sequence[int]):
@@ -195,7 +195,7 @@ def sim(kwd_n: torch.Tensor, utt_n: torch.Tensor, want_f32: bool, want_f16: bool
 
 
 def stem(feat_f16: torch.Tensor, Tu: int, w_packed: torch.Tensor, bias: torch.Tensor, out_mode: int,
-         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+         out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
     """feat_f16 fp16 [..., C, Tk, pitch] -> NCHW fp32 [N,64,Ho,Wo] or channels_last bf16 (logical
     shape [N,64,Ho,Wo], physical [N,Ho,Wo,64])."""
     lib = _lib.load()
@@ -207,9 +207,13 @@ def stem(feat_f16: torch.Tensor, Tu: int, w_packed: torch.Tensor, bias: torch.Te
             out = torch.empty((pairs, 64, Ho, Wo), dtype=torch.float32, device=feat_f16.device)
         else:
             out = torch.empty((pairs, Ho, Wo, 64), dtype=torch.bfloat16, device=feat_f16.device)
+    ws_bytes = lib.kws_stem_workspace_bytes(pairs, Cc, Tk, Tu)
+    if ws_bytes and (workspace is None or workspace.numel() * workspace.element_size() < ws_bytes):
+        workspace = torch.empty(ws_bytes // 4, dtype=torch.float32, device=feat_f16.device)
     check(lib.kws_stem(_cuda(feat_f16, "feat_f16", torch.float16), pairs, Cc, Tk, Tu, pitch,
                        _cuda(w_packed, "w_packed", torch.float16), _cuda(bias, "bias", torch.float32), out_mode,
-                       _cuda(out, "out"), _stream()), "kws_stem")
+                       _cuda(out, "out"), _cuda(workspace, "workspace") if ws_bytes else 0, _stream()), "kws_stem",
+          launches=(Cc + 15) // 16)
     if out_mode == STEM_OUT_NHWC_BF16:
         return out.permute(0, 3, 1, 2)  # channels_last view
     return out

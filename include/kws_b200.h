@@ -137,9 +137,11 @@ int kws_sim(const void* kwd_n, const void* utt_n, int C, int K, int U, int Tk, i
  * src/efficient_kws/resnet.py:38,53).
  *   feat_f16 fp16 [pairs,C,Tk,pitch16]; w_packed/bias from kws_pack_stem_weights
  *   out: [pairs,64,Ho,Wo] fp32 or [pairs,Ho,Wo,64] bf16, Ho=ceil(Tk/2), Wo=ceil(Tu/2)
- *   Requires C <= 16 (one 16-channel group per pass).                           */
+ *   C <= 16 runs in one launch.  C > 16 runs one launch per 16-channel group and chains the
+ *   partial sums through `workspace` (fp32, kws_stem_workspace_bytes(); may be NULL for C <= 16). */
 int kws_stem(const void* feat_f16, int pairs, int C, int Tk, int Tu, int pitch16, const void* w_packed,
-             const float* bias, int out_mode, void* out, void* stream);
+             const float* bias, int out_mode, void* out, void* workspace, void* stream);
+size_t kws_stem_workspace_bytes(int pairs, int C, int Tk, int Tu);
 
 /* ---- scores ---------------------------------------------------------------- */
 

@@ -1,0 +1,89 @@
+"""CPU: the C-ABI library builds for sm_100a, loads, exports every symbol include/kws_b200.h
+declares, and rejects bad arguments before touching the device (no compute calls without a GPU)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "kws_b200.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(kws_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_expected_entry_points():
+    syms = declared_symbols()
+    for s in ("kws_abi_version", "kws_last_error", "kws_normalize_rows", "kws_mlp", "kws_temporal", "kws_sim",
+              "kws_stem", "kws_scores", "kws_topk"):
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    lib = C.CDLL(built_lib)
+    for s in declared_symbols():
+        assert hasattr(lib, s), f"{s} declared in include/kws_b200.h but not exported"
+
+
+def test_python_binding_mirrors_header(built_lib):
+    from enhance_cb_whisper_b200 import _lib
+
+    assert sorted(_lib.SIGNATURES) == declared_symbols()
+    lib = _lib.load()
+    assert lib.kws_abi_version() == _lib.ABI_VERSION
+
+
+def test_library_is_sm100a_tcgen05(built_lib):
+    """SASS evidence of the Blackwell-native path: UTC*MMA (tcgen05.mma), LDTM (tcgen05.ld), UTMALDG (TMA)."""
+    out = subprocess.run(["cuobjdump", "-sass", built_lib], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump not available")
+    assert "sm_100a" in out.stdout
+    for mnem in ("UTCHMMA", "LDTM", "UTMALDG"):
+        assert mnem in out.stdout, f"{mnem} not found in SASS"
+
+
+def test_bad_arguments_are_rejected_without_a_device(built_lib):
+    from enhance_cb_whisper_b200 import _lib
+
+    lib = _lib.load()
+    # null pointers
+    assert lib.kws_sim(None, None, 1, 1, 1, 8, 8, 64, 0, None, None, 8, None) == -1
+    assert b"null" in lib.kws_last_error()
+    # Dk not a multiple of 64
+    one = C.c_void_p(16)
+    assert lib.kws_sim(one, one, 1, 1, 1, 8, 8, 48, 0, one, None, 8, None) == -1
+    assert b"Dk" in lib.kws_last_error()
+    # DIAG pairing needs U == K
+    assert lib.kws_sim(one, one, 1, 2, 3, 8, 8, 64, 1, one, None, 8, None) == -1
+    # MLP shape rules
+    assert lib.kws_mlp(one, 1, 1, 1, 100, 50, 64, 0, one, one, one, one, one, None, 1e-6, 0, one, None) == -1
+    assert b"multiple of 64" in lib.kws_last_error()
+    # top-k limits
+    assert lib.kws_topk(one, None, 10, 1, 0, 2000, one, one, None) == -1
+    with pytest.raises(_lib.KWSError):
+        _lib.check(-1, "kws_topk")
+
+
+def test_cpu_tensors_are_refused(built_lib):
+    import torch
+
+    from enhance_cb_whisper_b200 import ops
+
+    x = torch.zeros(1, 1, 4, 64)
+    with pytest.raises(ops.KWSError):
+        ops.normalize_rows(x, [0], None)
+
+
+def test_missing_library_fails_loudly(built_lib, monkeypatch):
+    from enhance_cb_whisper_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libkws_b200.so")
+    with pytest.raises(_lib.KWSError):
+        _lib.load()

@@ -1,0 +1,205 @@
+"""GPU: each sm_100a kernel, called through the C ABI, against torch arithmetic on the SAME
+quantised operands (isolates kernel errors from 16-bit rounding) and against the fp32 oracle."""
+import pytest
+import torch
+
+from oracle import kws_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops(built_lib, cuda_dev):
+    from enhance_cb_whisper_b200 import ops as _ops
+
+    return _ops
+
+
+def gen(dev, seed=1234):
+    return torch.Generator(device=dev).manual_seed(seed)
+
+
+def unit_rows(*shape, g, dev):
+    x = torch.randn(*shape, generator=g, device=dev)
+    return x / x.norm(dim=-1, keepdim=True)
+
+
+def maxerr(a, b):
+    return (a.float() - b.float()).abs().max().item()
+
+
+# ---- prep ---------------------------------------------------------------------------------
+def test_normalize_rows_selects_normalises_masks(ops, cuda_dev):
+    g = gen(cuda_dev)
+    B, Cin, T, D = 3, 5, 37, 384
+    x = torch.randn(B, Cin, T, D, generator=g, device=cuda_dev)
+    x[1, :, 30:] = 0  # zero-padded frames: norm clamps at eps, output stays 0
+    lidx = [4, 1, 2]
+    mask = (torch.rand(B, 3, T, generator=g, device=cuda_dev) > 0.2).float()
+    out = ops.normalize_rows(x, lidx, mask)
+    xs = x[:, lidx].permute(1, 0, 2, 3)
+    exp = xs / xs.norm(dim=-1, keepdim=True).clamp(min=1e-6) * mask.permute(1, 0, 2)[..., None]
+    assert out.shape == (3, B, T, D) and out.dtype == torch.float16
+    assert maxerr(out, exp) <= 1e-3
+    assert torch.equal(out[:, 1, 30:], torch.zeros_like(out[:, 1, 30:]))
+
+
+@pytest.mark.parametrize("d16", ["F16", "BF16"])
+def test_cast_rows16_is_bit_exact(ops, cuda_dev, d16):
+    g = gen(cuda_dev)
+    x = torch.randn(2, 4, 19, 128, generator=g, device=cuda_dev) * 3
+    code = getattr(ops, d16)
+    out = ops.cast_rows16(x, [3, 0], code)
+    exp = x[:, [3, 0]].permute(1, 0, 2, 3).to(ops.TORCH16[code]).reshape(2, 2 * 19, 128)
+    assert torch.equal(out, exp)
+
+
+def test_cast16_saturates_fp16(ops, cuda_dev):
+    x = torch.tensor([1e6, -1e6, 1.0, 65504.0], device=cuda_dev)
+    out = ops.cast16(x, ops.F16)
+    assert torch.equal(out.float(), torch.tensor([65504.0, -65504.0, 1.0, 65504.0], device=cuda_dev))
+
+
+# ---- similarity GEMM ------------------------------------------------------------------------
+@pytest.mark.parametrize("Cc,K,U,Tk,Tu,Dk", [(1, 1, 1, 16, 128, 64), (2, 3, 2, 22, 70, 64), (2, 2, 2, 150, 300, 128),
+                                             (1, 2, 1, 150, 1500, 384), (1, 1, 1, 75, 750, 64), (1, 1, 1, 1, 1, 64)])
+def test_sim_matches_matmul(ops, cuda_dev, Cc, K, U, Tk, Tu, Dk):
+    g = gen(cuda_dev)
+    kn = unit_rows(Cc, K, Tk, Dk, g=g, dev=cuda_dev).half()
+    un = unit_rows(Cc, U, Tu, Dk, g=g, dev=cuda_dev).half()
+    f32, f16 = ops.sim(kn, un, True, True)
+    exp = torch.einsum("ckid,cujd->kucij", kn.float(), un.float())
+    assert maxerr(f32, exp) <= 2e-4
+    assert maxerr(f16[..., :Tu], exp) <= 1e-3
+
+
+def test_sim_diag_pairing(ops, cuda_dev):
+    g = gen(cuda_dev)
+    Cc, K, Tk, Tu, Dk = 2, 3, 20, 70, 64
+    kn = unit_rows(Cc, K, Tk, Dk, g=g, dev=cuda_dev).half()
+    un = unit_rows(Cc, K, Tu, Dk, g=g, dev=cuda_dev).half()
+    f32, _ = ops.sim(kn, un, True, False, diag=True)
+    exp = torch.einsum("ckid,ckjd->kcij", kn.float(), un.float())
+    assert maxerr(f32, exp) <= 2e-4
+
+
+def test_sim_linearity_and_zero_rows(ops, cuda_dev):
+    """size-independent properties: zero operand rows give exactly 0; scaling an operand row by 2
+    scales its similarity row by exactly 2 (power-of-two scaling is exact in fp16/fp32)."""
+    g = gen(cuda_dev)
+    Cc, K, U, Tk, Tu, Dk = 1, 2, 2, 33, 140, 64
+    kn = unit_rows(Cc, K, Tk, Dk, g=g, dev=cuda_dev).half()
+    un = unit_rows(Cc, U, Tu, Dk, g=g, dev=cuda_dev).half()
+    kn[0, 1, 10:] = 0
+    a, _ = ops.sim(kn, un, True, False)
+    assert torch.equal(a[1, :, 0, 10:], torch.zeros_like(a[1, :, 0, 10:]))
+    kn2 = kn.clone()
+    kn2[0, 0, 5] *= 0.5
+    b, _ = ops.sim(kn2, un, True, False)
+    assert torch.equal(b[0, :, 0, 5], a[0, :, 0, 5] * 0.5)
+
+
+# ---- projector MLP ----------------------------------------------------------------------------
+@pytest.mark.parametrize("Cc,B,T,D,P,d16", [(2, 3, 50, 128, 64, "BF16"), (3, 2, 150, 768, 64, "F16"),
+                                            (1, 1, 300, 256, 32, "F16"), (1, 2, 7, 1280, 64, "F16")])
+def test_mlp_matches_same_quantisation_reference(ops, cuda_dev, Cc, B, T, D, P, d16):
+    g = gen(cuda_dev)
+    code = getattr(ops, d16)
+    tdt = ops.TORCH16[code]
+    H = D // 2
+    x = unit_rows(B, Cc, T, D, g=g, dev=cuda_dev)
+    w1 = torch.randn(Cc, H, D, generator=g, device=cuda_dev) * (4.0 / D ** 0.5)
+    b1 = torch.randn(Cc, H, generator=g, device=cuda_dev) * 0.05
+    w2 = torch.randn(Cc, P, H, generator=g, device=cuda_dev) / H ** 0.5
+    b2 = torch.randn(Cc, P, generator=g, device=cuda_dev) * 0.05
+    mask = (torch.rand(B, Cc, T, generator=g, device=cuda_dev) > 0.1).float()
+    xb = ops.cast_rows16(x, list(range(Cc)), code)
+    w1b, w2b = ops.cast16(w1, code), ops.cast16(w2, code)
+    raw = ops.mlp(xb, B, T, w1b, b1, w2b, b2, None, ops.MLP_OUT_RAW_F32)
+    xq = xb.float().view(Cc, B, T, D)
+    h = torch.relu(torch.einsum("cbtd,chd->cbth", xq, w1b.float()) + b1[:, None, None, :]).to(tdt).float()
+    exp = torch.einsum("cbth,cph->cbtp", h, w2b.float()) + b2[:, None, None, :]
+    assert maxerr(raw, exp) <= 2e-3
+    nrm = ops.mlp(xb, B, T, w1b, b1, w2b, b2, mask, ops.MLP_OUT_NORM_F16)
+    expn = exp / exp.norm(dim=-1, keepdim=True).clamp(min=1e-6) * mask.permute(1, 0, 2)[..., None]
+    assert maxerr(nrm, expn) <= 2e-3
+    # against the true fp32 MLP of the oracle (model.py:92-104): fp16 operands stay within 5e-3 of |out| ~ 1
+    hf = torch.relu(torch.einsum("bctd,chd->cbth", x, w1) + b1[:, None, None, :])
+    ef = torch.einsum("cbth,cph->cbtp", hf, w2) + b2[:, None, None, :]
+    assert maxerr(raw, ef) <= (2e-2 if d16 == "BF16" else 5e-3)
+
+
+# ---- LEF temporal projector -------------------------------------------------------------------
+@pytest.mark.parametrize("Cc,B,T,P", [(2, 3, 23, 64), (3, 2, 150, 64), (1, 1, 71, 32), (1, 2, 1, 64), (1, 1, 2, 64)])
+def test_temporal_matches_oracle(ops, cuda_dev, Cc, B, T, P):
+    g = gen(cuda_dev)
+    sd = O.make_weights("LEF", Cc, 128, P, seed=5)
+    proj = torch.randn(Cc, B, T, P, generator=g, device=cuda_dev)
+    st = lambda n: torch.stack([sd[f"time_projector.{i}.{n}"] for i in range(Cc)]).to(cuda_dev)
+    wf, bf = ops.fold_temporal_weights(st("0.weight"), st("0.bias"), st("1.weight"), st("1.bias"),
+                                       st("1.running_mean"), st("1.running_var"))
+    T2 = (T + 1) // 2
+    mask = (torch.rand(B, Cc, T2, generator=g, device=cuda_dev) > 0.1).float()
+    out = ops.temporal(proj, wf, bf, mask)
+    exp = torch.stack([O.project_time(proj[i].cpu(), sd, i) for i in range(Cc)]).to(cuda_dev)
+    exp = exp / exp.norm(dim=-1, keepdim=True).clamp(min=1e-6) * mask.permute(1, 0, 2)[..., None]
+    assert out.shape == (Cc, B, T2, P)
+    assert maxerr(out, exp) <= 1e-3
+
+
+# ---- stem ---------------------------------------------------------------------------------------
+def stem_expect(f16, Tu, sd):
+    """conv on the same fp16 features with the fp16-rounded BN-folded weights, fp64 accumulate."""
+    w = sd[O.STEM + "convolution.weight"].double()
+    gm, b = sd[O.STEM + "normalization.weight"].double(), sd[O.STEM + "normalization.bias"].double()
+    m, v = sd[O.STEM + "normalization.running_mean"].double(), sd[O.STEM + "normalization.running_var"].double()
+    s = gm / torch.sqrt(v + 1e-5)
+    wq = (w * s[:, None, None, None]).float().half().double()
+    x = f16[..., :Tu].double().flatten(0, -4)
+    y = torch.nn.functional.conv2d(x, wq, (b - m * s), stride=2, padding=3)
+    return torch.relu(y).float()
+
+
+def pack_stem(ops, sd):
+    return ops.pack_stem_weights(sd[O.STEM + "convolution.weight"], sd[O.STEM + "normalization.weight"],
+                                 sd[O.STEM + "normalization.bias"], sd[O.STEM + "normalization.running_mean"],
+                                 sd[O.STEM + "normalization.running_var"])
+
+
+@pytest.mark.parametrize("N,Cc,Tk,Tu", [(1, 3, 8, 40), (2, 3, 22, 70), (2, 12, 23, 301), (1, 16, 150, 1500),
+                                        (1, 4, 1, 1), (1, 32, 21, 135), (2, 20, 9, 260)])
+def test_stem_matches_conv(ops, cuda_dev, N, Cc, Tk, Tu):
+    g = gen(cuda_dev)
+    sd = {k: v.to(cuda_dev) for k, v in O.make_weights("L", Cc, 64, seed=9).items()}
+    pitch = ops.pitch_for(Tu)
+    f16 = (torch.rand(N, Cc, Tk, pitch, generator=g, device=cuda_dev) * 2 - 1).half()
+    wp, bias = pack_stem(ops, sd)
+    exp = stem_expect(f16, Tu, sd)
+    out = ops.stem(f16, Tu, wp, bias, ops.STEM_OUT_NCHW_F32)
+    assert out.shape == exp.shape
+    assert maxerr(out, exp) <= 2e-4 * max(1.0, Cc / 16)
+    o2 = ops.stem(f16, Tu, wp, bias, ops.STEM_OUT_NHWC_BF16)
+    assert maxerr(o2, exp) <= 2e-2 * max(1.0, exp.abs().max().item() / 4)
+
+
+# ---- scores + top-k -------------------------------------------------------------------------------
+def test_scores_and_detections(ops, cuda_dev):
+    g = gen(cuda_dev)
+    logits = torch.randn(1000, 2, generator=g, device=cuda_dev) * 3
+    hw = (torch.rand(1000, generator=g, device=cuda_dev) > 0.05).float()
+    sc, det = ops.scores(logits, hw, 0.5)
+    exp = logits.softmax(-1)[:, 1] * hw
+    assert maxerr(sc, exp) <= 1e-6
+    safe = (exp - 0.5).abs() > 1e-5
+    assert torch.equal(det.bool()[safe], (exp >= 0.5)[safe])
+
+
+@pytest.mark.parametrize("n,U,k", [(50, 3, 10), (1000, 4, 200), (7, 2, 7), (300, 1, 1)])
+def test_topk_matches_torch_with_index_tiebreak(ops, cuda_dev, n, U, k):
+    g = gen(cuda_dev)
+    sc = torch.randn(n, U, generator=g, device=cuda_dev)
+    sc[n // 2] = sc[0]  # exact ties -> lower id first
+    v, i = ops.topk(sc.contiguous(), k, None, 100)
+    order = torch.argsort(-sc.double() - 0.0, dim=0, stable=True)[:k]  # stable: lower index first on ties
+    assert torch.equal(v, torch.gather(sc, 0, order))
+    assert torch.equal(i.long(), order + 100)
