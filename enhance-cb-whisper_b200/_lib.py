@@ -38,6 +38,8 @@ SIGNATURES = {
     "kws_sim": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "kws_stem": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "kws_stem_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "kws_sim_stem": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "kws_sim_stem_supported": (_i, [_i, _i, _i, _i]),
     "kws_scores": (_i, [_vp, _vp, _sz, _f, _vp, _vp, _vp]),
     "kws_topk": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
 }

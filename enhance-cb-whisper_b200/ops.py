@@ -219,6 +219,35 @@ def stem(feat_f16: torch.Tensor, Tu: int, w_packed: torch.Tensor, bias: torch.Te
     return out
 
 
+def sim_stem_supported(Cc: int, Tk: int, Tu: int, Dk: int) -> bool:
+    return bool(_lib.load().kws_sim_stem_supported(Cc, Tk, Tu, Dk))
+
+
+def sim_stem(kwd_n: torch.Tensor, utt_n: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, out_mode: int,
+             diag: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Fused similarity + stem.  kwd_n fp16 [C,K,Tk,Dk], utt_n fp16 [C,U,Tu,Dk] -> stem activation of all
+    K x U pairs (pair = k * U + u; DIAG: pair = k): NCHW fp32 [N,64,Ho,Wo] or channels_last bf16."""
+    lib = _lib.load()
+    Cc, K, Tk, Dk = kwd_n.shape
+    Cu, U, Tu, Dku = utt_n.shape
+    if Cc != Cu or Dk != Dku:
+        raise KWSError(f"operand mismatch: kwd {tuple(kwd_n.shape)} vs utt {tuple(utt_n.shape)}")
+    pairs = K if diag else K * U
+    Ho, Wo = (Tk + 1) // 2, (Tu + 1) // 2
+    if out is None:
+        if out_mode == STEM_OUT_NCHW_F32:
+            out = torch.empty((pairs, 64, Ho, Wo), dtype=torch.float32, device=kwd_n.device)
+        else:
+            out = torch.empty((pairs, Ho, Wo, 64), dtype=torch.bfloat16, device=kwd_n.device)
+    check(lib.kws_sim_stem(_cuda(kwd_n, "kwd_n", torch.float16), _cuda(utt_n, "utt_n", torch.float16), Cc, K, U, Tk,
+                           Tu, Dk, PAIRS_DIAG if diag else PAIRS_ALL, _cuda(w_packed, "w_packed", torch.float16),
+                           _cuda(bias, "bias", torch.float32), out_mode, _cuda(out, "out"), _stream()),
+          "kws_sim_stem")
+    if out_mode == STEM_OUT_NHWC_BF16:
+        return out.permute(0, 3, 1, 2)
+    return out
+
+
 # ---- scores ------------------------------------------------------------------------
 def scores(logits: torch.Tensor, hotword_mask: Optional[torch.Tensor], threshold: float):
     """logits fp32 [n,2] -> (scores fp32 [n], detections uint8 [n])"""

@@ -143,6 +143,17 @@ int kws_stem(const void* feat_f16, int pairs, int C, int Tk, int Tu, int pitch16
              const float* bias, int out_mode, void* out, void* workspace, void* stream);
 size_t kws_stem_workspace_bytes(int pairs, int C, int Tk, int Tu);
 
+/* Fused similarity + stem: kws_sim followed by kws_stem without the [pairs,C,Tk,Tu] tensor ever
+ * reaching HBM -- similarity tiles go TMEM -> fp16 shared-memory ring -> stem MMAs in one kernel
+ * (replaces model.py:174-191,:217 and HF modeling_resnet.py:39-54 via resnet.py:38,53 together).
+ *   kwd_n fp16 [C,K,Tk,Dk], utt_n fp16 [C,U,Tu,Dk] (prepared operands, mask folded)
+ *   w_packed/bias from kws_pack_stem_weights; pair_mode / out_mode / out as kws_sim / kws_stem
+ *   Requires C <= 12 and Dk % 64 == 0 (kws_sim_stem_supported() != 0); other shapes use
+ *   kws_sim + kws_stem.                                                                     */
+int kws_sim_stem(const void* kwd_n, const void* utt_n, int C, int K, int U, int Tk, int Tu, int Dk, int pair_mode,
+                 const void* w_packed, const float* bias, int out_mode, void* out, void* stream);
+int kws_sim_stem_supported(int C, int Tk, int Tu, int Dk);
+
 /* ---- scores ---------------------------------------------------------------- */
 
 /* Detection score softmax(logits)[:,1] * hotword_mask (model.py:783-795) and

@@ -182,6 +182,52 @@ def test_stem_matches_conv(ops, cuda_dev, N, Cc, Tk, Tu):
     assert maxerr(o2, exp) <= 2e-2 * max(1.0, exp.abs().max().item() / 4)
 
 
+# ---- fused similarity + stem ----------------------------------------------------------------------
+@pytest.mark.parametrize("Cc,K,U,Tk,Tu,Dk", [(3, 2, 2, 22, 70, 64), (12, 2, 1, 150, 1500, 64), (4, 1, 2, 150, 300, 384),
+                                             (12, 3, 2, 75, 750, 64), (1, 1, 1, 1, 1, 64), (5, 2, 3, 37, 251, 128),
+                                             (8, 1, 1, 9, 123, 64), (2, 1, 1, 150, 122, 64)])
+def test_sim_stem_fused_matches_unfused_and_conv(ops, cuda_dev, Cc, K, U, Tk, Tu, Dk):
+    """kws_sim_stem == kws_stem(kws_sim(.)) up to fp32 summation order, and == conv2d on the fp16 similarity."""
+    g = gen(cuda_dev)
+    kn = unit_rows(Cc, K, Tk, Dk, g=g, dev=cuda_dev).half()
+    un = unit_rows(Cc, U, Tu, Dk, g=g, dev=cuda_dev).half()
+    kn[:, 0, Tk // 2:] = 0  # masked (zeroed) keyword frames
+    un[:, -1, (2 * Tu) // 3:] = 0
+    sd = {k: v.to(cuda_dev) for k, v in O.make_weights("L", Cc, 64, seed=9).items()}
+    wp, bias = pack_stem(ops, sd)
+    assert ops.sim_stem_supported(Cc, Tk, Tu, Dk)
+    _, f16 = ops.sim(kn, un, False, True)
+    exp = stem_expect(f16, Tu, sd)
+    ref = ops.stem(f16, Tu, wp, bias, ops.STEM_OUT_NCHW_F32)
+    out = ops.sim_stem(kn, un, wp, bias, ops.STEM_OUT_NCHW_F32)
+    assert out.shape == exp.shape == ref.shape
+    tol = 3e-4 * max(1.0, exp.abs().max().item())
+    assert maxerr(out, exp) <= tol
+    assert maxerr(out, ref) <= tol
+    o2 = ops.sim_stem(kn, un, wp, bias, ops.STEM_OUT_NHWC_BF16)
+    assert maxerr(o2, exp) <= 2e-2 * max(1.0, exp.abs().max().item() / 4)
+
+
+def test_sim_stem_fused_diag_and_many_items(ops, cuda_dev):
+    """More items than SMs (persistent loop, barrier phases across items) and the DIAG pairing."""
+    g = gen(cuda_dev)
+    Cc, K, U, Tk, Tu, Dk = 12, 40, 5, 30, 260, 64  # 200 pairs x 3 column tiles = 600 items
+    kn = unit_rows(Cc, K, Tk, Dk, g=g, dev=cuda_dev).half()
+    un = unit_rows(Cc, U, Tu, Dk, g=g, dev=cuda_dev).half()
+    sd = {k: v.to(cuda_dev) for k, v in O.make_weights("L", Cc, 64, seed=3).items()}
+    wp, bias = pack_stem(ops, sd)
+    _, f16 = ops.sim(kn, un, False, True)
+    ref = ops.stem(f16, Tu, wp, bias, ops.STEM_OUT_NCHW_F32)
+    out = ops.sim_stem(kn, un, wp, bias, ops.STEM_OUT_NCHW_F32)
+    assert maxerr(out, ref) <= 3e-4 * max(1.0, ref.abs().max().item())
+    un2 = unit_rows(Cc, K, Tu, Dk, g=g, dev=cuda_dev).half()
+    _, f16d = ops.sim(kn, un2, False, True, diag=True)
+    refd = ops.stem(f16d, Tu, wp, bias, ops.STEM_OUT_NCHW_F32)
+    outd = ops.sim_stem(kn, un2, wp, bias, ops.STEM_OUT_NCHW_F32, diag=True)
+    assert outd.shape == refd.shape
+    assert maxerr(outd, refd) <= 3e-4 * max(1.0, refd.abs().max().item())
+
+
 # ---- scores + top-k -------------------------------------------------------------------------------
 def test_scores_and_detections(ops, cuda_dev):
     g = gen(cuda_dev)
