@@ -149,11 +149,15 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tmem_base != 0) {  // all 512 columns of this SM's TMEM: the allocation can only start at column 0
+    if (threadIdx.x == 0) printf("[kws] unexpected TMEM base 0x%x\n", tmem_base);
+    __trap();
+  }
   const int stages_per_chunk = p.C * p.nkb;
 
   if (warp == 0) {
     // ===================== TMA producer: similarity operands =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (long long it = blockIdx.x; it < p.num_items; it += gridDim.x) {
@@ -175,85 +179,91 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc_sim = make_idesc_f16(128, 16, 0);
-      const uint32_t idesc_stem = make_idesc_f16(128, F_OC, 0);
-      const uint64_t adesc0 = make_smem_desc(smem_u32(s_ring), 4 * F_BLOCK, 128, LAYOUT_NONE);
-      const uint64_t bdesc0 = make_smem_desc(smem_u32(s_w), F_OC * 16, 128, LAYOUT_NONE);
-      // similarity cursor (runs ahead of the stem cursor, across items, as far as the two TMEM
-      // regions and the operand stages allow)
-      long long s_it = blockIdx.x;
-      int s_chunk = 0, s_stage = 0;
-      uint32_t s_g = 0;  // similarity chunks fully issued so far (global)
-      int o_stage = 0;
-      uint32_t o_phase = 0;
-      auto sim_try = [&](bool blocking) -> bool {
-        if (s_it >= p.num_items) return false;
-        const uint32_t buf = s_g & 1;
-        if (s_stage == 0 && !mbar_poll(&sempty[buf], ((s_g >> 1) & 1) ^ 1, blocking, 500 + buf)) return false;
-        if (!mbar_poll(&ofull[o_stage], o_phase, blocking, 300 + o_stage)) return false;
-        tc_fence_after();
-        const int c = s_stage / p.nkb, kb = s_stage - c * p.nkb;
-        const uint32_t d = tmem_base + F_TMEM_SIM + buf * F_SIM_COLS + c * 16;
-        const uint32_t sa = smem_u32(s_ops + (size_t)o_stage * F_STAGE);
-        const uint64_t adesc = make_smem_desc(sa, 16, 1024, LAYOUT_SW128);
-        const uint64_t bdesc = make_smem_desc(sa + F_A_BYTES, 16, 1024, LAYOUT_SW128);
+    // The whole warp runs this loop with identical (warp-uniform) values; only lane 0 executes the
+    // tcgen05 instructions (predicated inside the asm), so descriptor arithmetic stays in uniform
+    // registers and one MMA costs a handful of issue slots.
+    if (elect_one()) {
+    const uint32_t idesc_sim = make_idesc_f16(128, 16, 0);
+    const uint32_t idesc_stem = make_idesc_f16(128, F_OC, 0);
+    const uint32_t ops_u32 = smem_u32(s_ops);
+    const uint64_t adesc0 = make_smem_desc(smem_u32(s_ring), 4 * F_BLOCK, 128, LAYOUT_NONE);
+    const uint64_t bdesc0 = make_smem_desc(smem_u32(s_w), F_OC * 16, 128, LAYOUT_NONE);
+    const uint64_t sdesc0 = make_smem_desc(0, 16, 1024, LAYOUT_SW128);
+    // similarity cursor: runs ahead of the stem cursor (across items) by about one chunk
+    long long s_it = blockIdx.x;
+    int s_chunk = 0, s_stage = 0;
+    uint32_t s_g = 0;  // similarity chunks fully issued so far (global)
+    int o_stage = 0;
+    uint32_t o_phase = 0;
+    auto sim_issue = [&]() {  // one operand stage = 4 MMAs of one layer / k-block
+      const uint32_t buf = s_g & 1;
+      if (s_stage == 0) mbar_wait(&sempty[buf], ((s_g >> 1) & 1) ^ 1, 500 + buf);
+      mbar_wait(&ofull[o_stage], o_phase, 300 + o_stage);
+      tc_fence_after();
+      const int c = s_stage / p.nkb, kb = s_stage - c * p.nkb;
+      const uint32_t d = F_TMEM_SIM + buf * F_SIM_COLS + c * 16;  // TMEM base is 0 (checked at start)
+      const uint32_t sa = ops_u32 + o_stage * F_STAGE;
+      const uint64_t adesc = sdesc0 + (uint64_t)(sa >> 4);
+      const uint64_t bdesc = adesc + (uint64_t)(F_A_BYTES >> 4);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16(d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc_sim, (kb | k) != 0);
-        umma_commit(&oempty[o_stage]);
-        if (++o_stage == F_NS) o_stage = 0, o_phase ^= 1;
-        if (++s_stage == stages_per_chunk) {
-          umma_commit(&sfull[buf]);
-          s_stage = 0;
-          ++s_g;
-          if (++s_chunk == p.n_chunks) s_chunk = 0, s_it += gridDim.x;
-        }
-        return true;
-      };
-
-      uint32_t g_chunk0 = 0;  // global index of the current item's chunk 0
-      uint32_t qbase = 0;     // global index of the current item's quantum 0
-      uint32_t acc_seq = 0;   // global stem step counter -> accumulator buffer
-      for (long long it = blockIdx.x; it < p.num_items; it += gridDim.x) {
-        int waited = 0;  // quanta of this item known to be in the ring
-        for (int P = 0; P < p.nP; ++P, ++acc_seq) {
-          // the chunk holding quantum P+2 must have been issued (it usually was, long ago)
-          int need_chunk = (P + 2) >> 2;
-          if (need_chunk > p.n_chunks - 1) need_chunk = p.n_chunks - 1;
-          while (s_g <= g_chunk0 + (uint32_t)need_chunk)
-            if (!sim_try(true)) break;
-          const uint32_t acc = acc_seq & 1;
-          mbar_wait(&aempty[acc], ((acc_seq >> 1) & 1) ^ 1, 200 + acc);
-          while (waited <= P + 2 && waited < p.nQ) {
-            const uint32_t G = qbase + waited;
-            mbar_wait(&qfull[G & 3], (G >> 2) & 1, 400 + (int)(G & 3));
-            ++waited;
-          }
-          tc_fence_after();
-          const uint32_t d = tmem_base + acc * F_OC;
-          const uint32_t slot_base = 2 * (qbase + P);
-#pragma unroll
-          for (int di = 0; di < 7; ++di) {
-            const uint32_t slot0 = (slot_base + (di >> 1)) & (F_NR - 1);
-            const uint64_t a_row = adesc0 + (uint64_t)(((((di + 1) & 1) * 2 * F_BLOCK) + slot0 * 1024) >> 4);
-            const uint64_t b_row = bdesc0 + (uint64_t)((di * 7 * F_TAP_BYTES) >> 4);
-#pragma unroll
-            for (int dj = 0; dj < 7; ++dj) {
-              umma_f16(d, a_row + (uint64_t)((((dj & 1) * F_BLOCK) + (dj >> 1) * 16) >> 4),
-                       b_row + (uint64_t)((dj * F_TAP_BYTES) >> 4), idesc_stem, (di | dj) != 0);
-            }
-            sim_try(false);
-          }
-          umma_commit(&qempty[(qbase + P) & 3]);  // quantum P is dead once these MMAs retire
-          umma_commit(&afull[acc]);
-        }
-        // the two tail quanta were read by the last step only
-        for (int q = p.nP; q < p.nQ; ++q) umma_commit(&qempty[(qbase + q) & 3]);
-        qbase += p.nQ;
-        g_chunk0 += p.n_chunks;
+      for (int k = 0; k < 4; ++k)
+        umma_f16(d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc_sim, (kb | k) != 0);
+      umma_commit(&oempty[o_stage]);
+      if (++o_stage == F_NS) o_stage = 0, o_phase ^= 1;
+      if (++s_stage == stages_per_chunk) {
+        umma_commit(&sfull[buf]);
+        s_stage = 0;
+        ++s_g;
+        if (++s_chunk == p.n_chunks) s_chunk = 0, s_it += gridDim.x;
       }
+    };
+
+    uint32_t g_chunk0 = 0;  // global index of the current item's chunk 0
+    uint32_t qbase = 0;     // global index of the current item's quantum 0
+    uint32_t acc_seq = 0;   // global stem step counter -> accumulator buffer
+    for (long long it = blockIdx.x; it < p.num_items; it += gridDim.x) {
+      int waited = 0;  // quanta of this item known to be in the ring
+      for (int P = 0; P < p.nP; ++P, ++acc_seq) {
+        // chunks: `need` holds quantum P+2 and must be issued now; `ahead` (one chunk further,
+        // possibly chunk 0 of the next item) is issued one stage per tap group while the stem runs
+        int need = (P + 2) >> 2;
+        if (need > p.n_chunks - 1) need = p.n_chunks - 1;
+        int ahead = ((P + 2) >> 2) + 1;
+        if (ahead > p.n_chunks) ahead = p.n_chunks;
+        const uint32_t g_need = g_chunk0 + (uint32_t)need, g_ahead = g_chunk0 + (uint32_t)ahead;
+        while (s_g <= g_need && s_it < p.num_items) sim_issue();
+        const uint32_t acc = acc_seq & 1;
+        mbar_wait(&aempty[acc], ((acc_seq >> 1) & 1) ^ 1, 200 + acc);
+        while (waited <= P + 2 && waited < p.nQ) {
+          const uint32_t G = qbase + waited;
+          mbar_wait(&qfull[G & 3], (G >> 2) & 1, 400 + (int)(G & 3));
+          ++waited;
+        }
+        tc_fence_after();
+        const uint32_t d = acc * F_OC;
+        const uint32_t slot_base = 2 * (qbase + P);
+#pragma unroll
+        for (int di = 0; di < 7; ++di) {
+          const uint32_t slot0 = (slot_base + (di >> 1)) & (F_NR - 1);
+          const uint64_t a_row = adesc0 + (uint64_t)(((((di + 1) & 1) * 2 * F_BLOCK) >> 4) + slot0 * 64);
+          const uint64_t b_row = bdesc0 + (uint64_t)((di * 7 * F_TAP_BYTES) >> 4);
+#pragma unroll
+          for (int dj = 0; dj < 7; ++dj) {
+            umma_f16(d, a_row + (uint64_t)((((dj & 1) * F_BLOCK) + (dj >> 1) * 16) >> 4),
+                       b_row + (uint64_t)((dj * F_TAP_BYTES) >> 4), idesc_stem, (di | dj) != 0);
+          }
+          if (s_g <= g_ahead && s_it < p.num_items) sim_issue();
+        }
+        umma_commit(&qempty[(qbase + P) & 3]);  // quantum P is dead once these MMAs retire
+        umma_commit(&afull[acc]);
+      }
+      // the two tail quanta were read by the last step only
+      for (int q = p.nP; q < p.nQ; ++q) umma_commit(&qempty[(qbase + q) & 3]);
+      qbase += p.nQ;
+      g_chunk0 += p.n_chunks;
     }
+    }
+    __syncwarp();
   } else if (warp >= 4 && warp < 8) {
     // ===================== stem epilogue =====================
     const int q = warp & 3;

@@ -129,7 +129,7 @@ kws_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (long long it = blockIdx.x; it < p.num_items; it += gridDim.x) {
@@ -147,7 +147,7 @@ kws_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       uint32_t iter = 0;

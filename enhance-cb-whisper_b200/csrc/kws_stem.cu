@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) kws_stem_kernel(const StemPar
 
   if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = make_idesc_f16(TILE_OJ, OC, 0);
       const uint64_t adesc0 = make_smem_desc(smem_u32(s_ring), CHUNK_BYTES, 128, LAYOUT_NONE);
       const uint64_t bdesc0 = make_smem_desc(smem_u32(s_w), OC * 16, 128, LAYOUT_NONE);

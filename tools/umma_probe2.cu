@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(192, 1) probe_kernel(Case c, long long* out_cy
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  if (warp == 1 && lane == 0) {
+  if (warp == 1 && elect_one()) {
     const uint32_t idesc = make_idesc_f16(128, c.N, 0);
     const uint32_t sa = smem_u32(base), sb = smem_u32(base + 64 * 1024);
     const uint64_t adesc = make_smem_desc(sa, c.a_lbo, c.a_sbo, c.a_layout);
