@@ -62,6 +62,7 @@ struct FusedParams {
   int n_chunks;  // similarity chunks (16 input rows) per item = ceil(nQ / 4)
   int diag;
   long long num_items;
+  long long* dbg;  // optional [grid][8] cycle counters of the MMA issuer (development aid), or null
 };
 
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
@@ -195,10 +196,12 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
     uint32_t s_g = 0;  // similarity chunks fully issued so far (global)
     int o_stage = 0;
     uint32_t o_phase = 0;
-    auto sim_issue = [&]() {  // one operand stage = 4 MMAs of one layer / k-block
+    // one operand stage = 4 MMAs of one layer / k-block; non-blocking calls return false when the
+    // TMEM region or the operands are not there yet (the stem MMAs go on, the call is retried)
+    auto sim_issue = [&](bool blocking) -> bool {
       const uint32_t buf = s_g & 1;
-      if (s_stage == 0) mbar_wait(&sempty[buf], ((s_g >> 1) & 1) ^ 1, 500 + buf);
-      mbar_wait(&ofull[o_stage], o_phase, 300 + o_stage);
+      if (s_stage == 0 && !mbar_poll(&sempty[buf], ((s_g >> 1) & 1) ^ 1, blocking, 500 + buf)) return false;
+      if (!mbar_poll(&ofull[o_stage], o_phase, blocking, 300 + o_stage)) return false;
       tc_fence_after();
       const int c = s_stage / p.nkb, kb = s_stage - c * p.nkb;
       const uint32_t d = F_TMEM_SIM + buf * F_SIM_COLS + c * 16;  // TMEM base is 0 (checked at start)
@@ -216,11 +219,14 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
         ++s_g;
         if (++s_chunk == p.n_chunks) s_chunk = 0, s_it += gridDim.x;
       }
+      return true;
     };
 
     uint32_t g_chunk0 = 0;  // global index of the current item's chunk 0
     uint32_t qbase = 0;     // global index of the current item's quantum 0
     uint32_t acc_seq = 0;   // global stem step counter -> accumulator buffer
+    long long tm_sim = 0, tm_acc = 0, tm_q = 0, tm_issue = 0;
+    const long long tm_start = clock64();
     for (long long it = blockIdx.x; it < p.num_items; it += gridDim.x) {
       int waited = 0;  // quanta of this item known to be in the ring
       for (int P = 0; P < p.nP; ++P, ++acc_seq) {
@@ -231,14 +237,19 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
         int ahead = ((P + 2) >> 2) + 1;
         if (ahead > p.n_chunks) ahead = p.n_chunks;
         const uint32_t g_need = g_chunk0 + (uint32_t)need, g_ahead = g_chunk0 + (uint32_t)ahead;
-        while (s_g <= g_need && s_it < p.num_items) sim_issue();
+        const long long t0 = clock64();
+        while (s_g <= g_need && s_it < p.num_items) sim_issue(true);
+        const long long t1 = clock64();
         const uint32_t acc = acc_seq & 1;
         mbar_wait(&aempty[acc], ((acc_seq >> 1) & 1) ^ 1, 200 + acc);
+        const long long t2 = clock64();
         while (waited <= P + 2 && waited < p.nQ) {
           const uint32_t G = qbase + waited;
           mbar_wait(&qfull[G & 3], (G >> 2) & 1, 400 + (int)(G & 3));
           ++waited;
         }
+        const long long t3 = clock64();
+        tm_sim += t1 - t0, tm_acc += t2 - t1, tm_q += t3 - t2;
         tc_fence_after();
         const uint32_t d = acc * F_OC;
         const uint32_t slot_base = 2 * (qbase + P);
@@ -252,15 +263,20 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
             umma_f16(d, a_row + (uint64_t)((((dj & 1) * F_BLOCK) + (dj >> 1) * 16) >> 4),
                        b_row + (uint64_t)((dj * F_TAP_BYTES) >> 4), idesc_stem, (di | dj) != 0);
           }
-          if (s_g <= g_ahead && s_it < p.num_items) sim_issue();
+          if (s_g <= g_ahead && s_it < p.num_items) sim_issue(false);
         }
         umma_commit(&qempty[(qbase + P) & 3]);  // quantum P is dead once these MMAs retire
         umma_commit(&afull[acc]);
+        tm_issue += clock64() - t3;
       }
       // the two tail quanta were read by the last step only
       for (int q = p.nP; q < p.nQ; ++q) umma_commit(&qempty[(qbase + q) & 3]);
       qbase += p.nQ;
       g_chunk0 += p.n_chunks;
+    }
+    if (p.dbg) {
+      long long* o = p.dbg + (size_t)blockIdx.x * 8;
+      o[0] = clock64() - tm_start, o[1] = tm_sim, o[2] = tm_acc, o[3] = tm_q, o[4] = tm_issue;
     }
     }
     __syncwarp();
@@ -388,6 +404,10 @@ static_assert(F_SMEM <= 232448, "fused kernel exceeds the 227 KB shared-memory l
 
 using namespace kws;
 
+static long long* g_fused_dbg = nullptr;
+// development aid (not part of the public header): device buffer [148][8] receiving the issuer's cycle counters
+extern "C" void kws_debug_set_fused_counters(long long* dev_buf) { g_fused_dbg = dev_buf; }
+
 extern "C" int kws_sim_stem_supported(int C, int Tk, int Tu, int Dk) {
   return C > 0 && C <= F_MAX_C && Dk >= 64 && Dk % 64 == 0 && Tk > 0 && Tu > 0;
 }
@@ -440,6 +460,7 @@ extern "C" int kws_sim_stem(const void* kwd_n, const void* utt_n, int C, int K, 
   long long grid = p.num_items;
   const int sms = sm_count();
   if (grid > sms) grid = sms;
+  p.dbg = g_fused_dbg;
   kws_fused_kernel<<<(int)grid, F_THREADS, F_SMEM, (cudaStream_t)stream>>>(mu, mk, p);
   KWS_CUDA(cudaGetLastError());
   return 0;

@@ -1,0 +1,26 @@
+"""Development aid: per-CTA cycle breakdown of the fused kernel's MMA issuer (waits vs issue)."""
+import ctypes, os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from enhance_cb_whisper_b200 import ops, _lib
+
+dev = torch.device("cuda:0")
+g = torch.Generator(device=dev).manual_seed(7)
+Cc, K, U, Tk, Tu, P = 12, 74, 2, 150, 1500, 64
+unit = lambda *s: torch.nn.functional.normalize(torch.randn(*s, generator=g, device=dev), dim=-1)
+kn, un = unit(Cc, K, Tk, P).half(), unit(Cc, U, Tu, P).half()
+wp, bias = ops.pack_stem_weights(torch.randn(64, Cc, 7, 7, generator=g, device=dev) * 0.05, torch.ones(64, device=dev),
+                                 torch.zeros(64, device=dev), torch.zeros(64, device=dev), torch.ones(64, device=dev))
+out = torch.empty(K * U, 75, 750, 64, dtype=torch.bfloat16, device=dev)
+ops.sim_stem(kn, un, wp, bias, ops.STEM_OUT_NHWC_BF16, out=out)
+buf = torch.zeros(148, 8, dtype=torch.int64, device=dev)
+lib = _lib.load()
+lib.kws_debug_set_fused_counters.argtypes = [ctypes.c_void_p]
+lib.kws_debug_set_fused_counters(buf.data_ptr())
+ops.sim_stem(kn, un, wp, bias, ops.STEM_OUT_NHWC_BF16, out=out)
+torch.cuda.synchronize()
+lib.kws_debug_set_fused_counters(None)
+b = buf.double().mean(0).tolist()
+items = K * U * 13 / 148
+print(f"per item (mean over CTAs, {items:.1f} items/CTA): total {b[0]/items:.0f} cyc | deadline-sim wait {b[1]/items:.0f} | "
+      f"aempty wait {b[2]/items:.0f} | qfull wait {b[3]/items:.0f} | issue {b[4]/items:.0f}")
