@@ -56,7 +56,8 @@ struct FusedParams {
   const float* bias;  // [64]
   void* out;
   int out_mode;
-  int C, K, U, Tk, Tu, nkb, Ho, Wo, col_tiles;
+  int C, K, U, Tk, Tu, nkb, Ho, Wo, col_tiles;  // K, U: operand batch sizes (tensor-map extents)
+  int k0, u0, nk, nu;  // scored sub-range: keywords [k0, k0+nk) x utterances [u0, u0+nu); out pair = (k-k0)*nu + (u-u0)
   int nP;        // stem steps per item = ceil(Ho / 2)
   int nQ;        // quanta (4 input rows) converted per item = nP + 2
   int n_chunks;  // similarity chunks (16 input rows) per item = ceil(nQ / 4)
@@ -88,10 +89,11 @@ __device__ __forceinline__ ItemCoord decode_item(const FusedParams& p, long long
   r.pair = it / p.col_tiles;
   r.ct = (int)(it - r.pair * p.col_tiles);
   if (p.diag) {
-    r.kw = r.u = (int)r.pair;
+    r.kw = r.u = p.k0 + (int)r.pair;
   } else {
-    r.kw = (int)(r.pair / p.U);
-    r.u = (int)(r.pair - (long long)r.kw * p.U);
+    const int kl = (int)(r.pair / p.nu);
+    r.kw = p.k0 + kl;
+    r.u = p.u0 + (int)(r.pair - (long long)kl * p.nu);
   }
   return r;
 }
@@ -415,12 +417,22 @@ extern "C" int kws_sim_stem_supported(int C, int Tk, int Tu, int Dk) {
 extern "C" int kws_sim_stem(const void* kwd_n, const void* utt_n, int C, int K, int U, int Tk, int Tu, int Dk,
                             int pair_mode, const void* w_packed, const float* bias, int out_mode, void* out,
                             void* stream) {
+  return kws_sim_stem_range(kwd_n, utt_n, C, K, U, Tk, Tu, Dk, pair_mode, 0, K, 0, U, w_packed, bias, out_mode, out,
+                            stream);
+}
+
+extern "C" int kws_sim_stem_range(const void* kwd_n, const void* utt_n, int C, int K, int U, int Tk, int Tu, int Dk,
+                                  int pair_mode, int k0, int nk, int u0, int nu, const void* w_packed,
+                                  const float* bias, int out_mode, void* out, void* stream) {
   KWS_CHECK_ARG(kwd_n && utt_n && w_packed && bias && out, "sim_stem: null pointer");
   KWS_CHECK_ARG(C > 0 && K > 0 && U > 0 && Tk > 0 && Tu > 0, "sim_stem: non-positive dimension");
+  KWS_CHECK_ARG(k0 >= 0 && nk > 0 && k0 + nk <= K, "sim_stem: keyword range [%d,%d) outside [0,%d)", k0, k0 + nk, K);
+  KWS_CHECK_ARG(u0 >= 0 && nu > 0 && u0 + nu <= U, "sim_stem: utterance range [%d,%d) outside [0,%d)", u0, u0 + nu, U);
   KWS_CHECK_ARG(C <= F_MAX_C, "sim_stem: C=%d > %d layers (use kws_sim + kws_stem)", C, F_MAX_C);
   KWS_CHECK_ARG(Dk % 64 == 0 && Dk >= 64, "sim_stem: Dk=%d must be a multiple of 64", Dk);
   KWS_CHECK_ARG(pair_mode == KWS_PAIRS_ALL || pair_mode == KWS_PAIRS_DIAG, "sim_stem: bad pair_mode %d", pair_mode);
-  KWS_CHECK_ARG(pair_mode == KWS_PAIRS_ALL || U == K, "sim_stem: KWS_PAIRS_DIAG needs U == K (got K=%d U=%d)", K, U);
+  KWS_CHECK_ARG(pair_mode == KWS_PAIRS_ALL || (U == K && k0 == u0 && nk == nu),
+                "sim_stem: KWS_PAIRS_DIAG needs U == K and equal ranges (got K=%d U=%d)", K, U);
   KWS_CHECK_ARG(out_mode == KWS_STEM_OUT_NCHW_F32 || out_mode == KWS_STEM_OUT_NHWC_BF16, "sim_stem: bad out_mode %d",
                 out_mode);
   KWS_CHECK_ARG((reinterpret_cast<uintptr_t>(w_packed) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
@@ -448,6 +460,7 @@ extern "C" int kws_sim_stem(const void* kwd_n, const void* utt_n, int C, int K, 
   p.out = out;
   p.out_mode = out_mode;
   p.C = C, p.K = K, p.U = U, p.Tk = Tk, p.Tu = Tu, p.nkb = Dk / 64;
+  p.k0 = k0, p.u0 = u0, p.nk = nk, p.nu = nu;
   p.Ho = (Tk + 1) / 2;
   p.Wo = (Tu + 1) / 2;
   p.col_tiles = (p.Wo + F_TILE_OJ - 1) / F_TILE_OJ;
@@ -455,7 +468,7 @@ extern "C" int kws_sim_stem(const void* kwd_n, const void* utt_n, int C, int K, 
   p.nQ = p.nP + 2;
   p.n_chunks = (p.nQ + 3) / 4;
   p.diag = pair_mode == KWS_PAIRS_DIAG;
-  p.num_items = (long long)K * (p.diag ? 1 : U) * p.col_tiles;
+  p.num_items = (long long)nk * (p.diag ? 1 : nu) * p.col_tiles;
   KWS_CUDA(cudaFuncSetAttribute(kws_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
   long long grid = p.num_items;
   const int sms = sm_count();

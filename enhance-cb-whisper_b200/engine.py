@@ -124,8 +124,9 @@ class KWSEngine:
 
     # -- stage 2+3 over pair chunks -----------------------------------------------------
     def pair_chunks(self, K: int, U: int, Tk: int, Tu: int, max_pairs: int) -> Iterator[Tuple[int, int, int, int]]:
-        """Tile the K x U pair grid into (k0,k1,u0,u1) blocks of at most max_pairs pairs:
-        whole keyword ranges per utterance block so the keyword slab is reused."""
+        """Tile the K x U pair grid into (k0,k1,u0,u1) blocks of at most max_pairs pairs.  Blocks are
+        keyword-major (a run of keywords against a few utterances) so that the utterance tiles, the larger
+        operand, stay L2-resident while the keyword rows stream."""
         max_pairs = max(1, max_pairs)
         ub = max(1, min(U, max_pairs // max(1, min(K, max_pairs))))
         kb = max(1, min(K, max_pairs // ub))
@@ -133,31 +134,53 @@ class KWSEngine:
             for k0 in range(0, K, kb):
                 yield k0, min(K, k0 + kb), u0, min(U, u0 + ub)
 
+    def fused(self, Tk: int, Tu: int) -> bool:
+        """True when the single-kernel similarity+stem path covers this model (kws_sim_stem_supported)."""
+        return self.w.stem_w is not None and ops.sim_stem_supported(self.w.C, Tk, Tu, self.w.Dk)
+
     def hot_path(self, kwd_n: torch.Tensor, utt_n: torch.Tensor, out_mode: int, max_pairs: int = 1024,
-                 consume: Optional[Callable] = None, bufs: Optional[dict] = None):
+                 consume: Optional[Callable] = None, bufs: Optional[dict] = None,
+                 launch_events: Optional[list] = None):
         """Similarity + stem for all pairs, chunked.  ``consume(k0,k1,u0,u1,stem_out)`` receives the
         stem activation of each chunk ([pairs,64,Ho,Wo], pair = (k-k0)*(u1-u0) + (u-u0));
-        intermediate buffers are reused across chunks (``bufs``)."""
+        intermediate buffers are reused across chunks (``bufs``).  The fused kernel is used whenever it
+        supports the shape (the similarity tensor then never exists in HBM); otherwise kws_sim + kws_stem.
+        ``launch_events``: if a list, a (start, end) CUDA-event pair around every pair-kernel launch is
+        appended (bench.py reads per-launch durations from them)."""
         Cc, K, Tk, Dk = kwd_n.shape
         _, U, Tu, _ = utt_n.shape
         bufs = bufs if bufs is not None else {}
+        fused = self.fused(Tk, Tu)
+        Ho, Wo = (Tk + 1) // 2, (Tu + 1) // 2
+        f32 = out_mode == ops.STEM_OUT_NCHW_F32
         n = 0
         for k0, k1, u0, u1 in self.pair_chunks(K, U, Tk, Tu, max_pairs):
-            kk = kwd_n[:, k0:k1].contiguous() if (k0, k1) != (0, K) else kwd_n
-            uu = utt_n[:, u0:u1].contiguous() if (u0, u1) != (0, U) else utt_n
             np_ = (k1 - k0) * (u1 - u0)
-            key16 = ("f16", np_, Cc, Tk, Tu)
-            if key16 not in bufs:
-                bufs[key16] = torch.empty((k1 - k0, u1 - u0, Cc, Tk, ops.pitch_for(Tu)), dtype=torch.float16,
-                                          device=kwd_n.device)
-            _, f16 = ops.sim(kk, uu, want_f32=False, want_f16=True, out_f16=bufs[key16])
-            keyo = ("stem", np_, Tk, Tu, out_mode)
-            if keyo not in bufs:
-                Ho, Wo = (Tk + 1) // 2, (Tu + 1) // 2
-                shape = (np_, 64, Ho, Wo) if out_mode == ops.STEM_OUT_NCHW_F32 else (np_, Ho, Wo, 64)
-                bufs[keyo] = torch.empty(shape, dtype=torch.float32 if out_mode == ops.STEM_OUT_NCHW_F32
-                                         else torch.bfloat16, device=kwd_n.device)
-            st = ops.stem(f16, Tu, self.w.stem_w, self.w.stem_b, out_mode, out=bufs[keyo])
+            keyo = ("stem", max_pairs, Tk, Tu, out_mode)
+            if keyo not in bufs or bufs[keyo].numel() < np_ * 64 * Ho * Wo:
+                cap = max(np_, min(max_pairs, K * U))
+                bufs[keyo] = torch.empty(cap * 64 * Ho * Wo, dtype=torch.float32 if f32 else torch.bfloat16,
+                                         device=kwd_n.device)
+            if launch_events is not None:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
+            if fused:
+                st = ops.sim_stem(kwd_n, utt_n, self.w.stem_w, self.w.stem_b, out_mode, out=bufs[keyo],
+                                  k_range=(k0, k1), u_range=(u0, u1))
+            else:
+                kk = kwd_n[:, k0:k1].contiguous() if (k0, k1) != (0, K) else kwd_n
+                uu = utt_n[:, u0:u1].contiguous() if (u0, u1) != (0, U) else utt_n
+                key16 = ("f16", np_, Cc, Tk, Tu)
+                if key16 not in bufs:
+                    bufs[key16] = torch.empty((k1 - k0, u1 - u0, Cc, Tk, ops.pitch_for(Tu)), dtype=torch.float16,
+                                              device=kwd_n.device)
+                _, f16 = ops.sim(kk, uu, want_f32=False, want_f16=True, out_f16=bufs[key16])
+                shape = (np_, 64, Ho, Wo) if f32 else (np_, Ho, Wo, 64)
+                st = ops.stem(f16, Tu, self.w.stem_w, self.w.stem_b, out_mode,
+                              out=bufs[keyo][: np_ * 64 * Ho * Wo].view(shape))
+            if launch_events is not None:
+                ev[1].record()
+                launch_events.append(ev + (np_,))
             if consume is not None:
                 consume(k0, k1, u0, u1, st)
             n += np_

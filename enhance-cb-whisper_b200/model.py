@@ -175,11 +175,17 @@ class B200ForwardMixin:
         with torch.no_grad():
             kwd_n = eng.compress(kwd_features, kwd_mask, layer_idx)
             utt_n = eng.compress(utt_features, utt_mask, layer_idx)
-            f32, f16 = ops.sim(kwd_n, utt_n, want_f32=self.b200_return_features, want_f16=True, diag=diag)
-            Tu_s = utt_n.shape[2]
+            Tk_s, Tu_s = kwd_n.shape[2], utt_n.shape[2]
             lowp = self.b200_body_dtype != "float32"
-            st = ops.stem(f16, Tu_s, eng.w.stem_w, eng.w.stem_b,
-                          ops.STEM_OUT_NHWC_BF16 if lowp else ops.STEM_OUT_NCHW_F32)
+            out_mode = ops.STEM_OUT_NHWC_BF16 if lowp else ops.STEM_OUT_NCHW_F32
+            f32 = None
+            if not self.b200_return_features and eng.fused(Tk_s, Tu_s):
+                # KWSOutput.features is read by no caller of the reference; without it the
+                # similarity tensor never reaches HBM
+                st = ops.sim_stem(kwd_n, utt_n, eng.w.stem_w, eng.w.stem_b, out_mode, diag=diag)
+            else:
+                f32, f16 = ops.sim(kwd_n, utt_n, want_f32=self.b200_return_features, want_f16=True, diag=diag)
+                st = ops.stem(f16, Tu_s, eng.w.stem_w, eng.w.stem_b, out_mode)
             logits = self._body(st).float()
         features = None
         if f32 is not None:

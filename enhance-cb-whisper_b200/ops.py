@@ -224,28 +224,38 @@ def sim_stem_supported(Cc: int, Tk: int, Tu: int, Dk: int) -> bool:
 
 
 def sim_stem(kwd_n: torch.Tensor, utt_n: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, out_mode: int,
-             diag: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Fused similarity + stem.  kwd_n fp16 [C,K,Tk,Dk], utt_n fp16 [C,U,Tu,Dk] -> stem activation of all
-    K x U pairs (pair = k * U + u; DIAG: pair = k): NCHW fp32 [N,64,Ho,Wo] or channels_last bf16."""
+             diag: bool = False, out: Optional[torch.Tensor] = None, k_range: Optional[Tuple[int, int]] = None,
+             u_range: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+    """Fused similarity + stem.  kwd_n fp16 [C,K,Tk,Dk], utt_n fp16 [C,U,Tu,Dk] -> stem activation of the
+    pairs of keywords k_range=(k0,k1) x utterances u_range=(u0,u1) (default: all), pair = (k-k0)*(u1-u0) + (u-u0)
+    (DIAG: pair = k-k0): NCHW fp32 [N,64,Ho,Wo] or channels_last bf16.  ``out`` may be a larger reused
+    buffer (its first N pairs are written)."""
     lib = _lib.load()
     Cc, K, Tk, Dk = kwd_n.shape
     Cu, U, Tu, Dku = utt_n.shape
     if Cc != Cu or Dk != Dku:
         raise KWSError(f"operand mismatch: kwd {tuple(kwd_n.shape)} vs utt {tuple(utt_n.shape)}")
-    pairs = K if diag else K * U
+    k0, k1 = k_range if k_range is not None else (0, K)
+    u0, u1 = u_range if u_range is not None else (0, U)
+    pairs = (k1 - k0) if diag else (k1 - k0) * (u1 - u0)
     Ho, Wo = (Tk + 1) // 2, (Tu + 1) // 2
+    f32 = out_mode == STEM_OUT_NCHW_F32
     if out is None:
-        if out_mode == STEM_OUT_NCHW_F32:
-            out = torch.empty((pairs, 64, Ho, Wo), dtype=torch.float32, device=kwd_n.device)
-        else:
-            out = torch.empty((pairs, Ho, Wo, 64), dtype=torch.bfloat16, device=kwd_n.device)
-    check(lib.kws_sim_stem(_cuda(kwd_n, "kwd_n", torch.float16), _cuda(utt_n, "utt_n", torch.float16), Cc, K, U, Tk,
-                           Tu, Dk, PAIRS_DIAG if diag else PAIRS_ALL, _cuda(w_packed, "w_packed", torch.float16),
-                           _cuda(bias, "bias", torch.float32), out_mode, _cuda(out, "out"), _stream()),
-          "kws_sim_stem")
+        out = torch.empty((pairs, 64, Ho, Wo) if f32 else (pairs, Ho, Wo, 64),
+                          dtype=torch.float32 if f32 else torch.bfloat16, device=kwd_n.device)
+    else:
+        want = torch.float32 if f32 else torch.bfloat16
+        if out.dtype != want or out.numel() < pairs * 64 * Ho * Wo:
+            raise KWSError(f"out buffer too small / wrong dtype for {pairs} pairs")
+    check(lib.kws_sim_stem_range(_cuda(kwd_n, "kwd_n", torch.float16), _cuda(utt_n, "utt_n", torch.float16), Cc, K,
+                                 U, Tk, Tu, Dk, PAIRS_DIAG if diag else PAIRS_ALL, k0, k1 - k0, u0, u1 - u0,
+                                 _cuda(w_packed, "w_packed", torch.float16), _cuda(bias, "bias", torch.float32),
+                                 out_mode, _cuda(out, "out"), _stream()), "kws_sim_stem")
+    shape = (pairs, 64, Ho, Wo) if f32 else (pairs, Ho, Wo, 64)
+    view = out.view(-1)[: pairs * 64 * Ho * Wo].view(shape)
     if out_mode == STEM_OUT_NHWC_BF16:
-        return out.permute(0, 3, 1, 2)
-    return out
+        return view.permute(0, 3, 1, 2)
+    return view
 
 
 # ---- scores ------------------------------------------------------------------------

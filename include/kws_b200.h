@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define KWS_ABI_VERSION 1
+#define KWS_ABI_VERSION 2
 
 /* 16-bit operand formats (same encoding as the tcgen05 kind::f16 descriptor) */
 #define KWS_F16 0  /* IEEE half: 10-bit mantissa; for L2-normalised data and sane weights */
@@ -153,6 +153,14 @@ size_t kws_stem_workspace_bytes(int pairs, int C, int Tk, int Tu);
 int kws_sim_stem(const void* kwd_n, const void* utt_n, int C, int K, int U, int Tk, int Tu, int Dk, int pair_mode,
                  const void* w_packed, const float* bias, int out_mode, void* out, void* stream);
 int kws_sim_stem_supported(int C, int Tk, int Tu, int Dk);
+/* Same kernel over a sub-block of the pair grid: keywords [k0, k0+nk) x utterances [u0, u0+nu) of the
+ * resident operand banks (K, U stay the bank sizes).  out holds nk*nu pairs, pair = (k-k0)*nu + (u-u0)
+ * (KWS_PAIRS_DIAG: nk pairs, ranges must coincide).  This is how the batched replacement of the
+ * test_step group loop (model.py:769-780) streams a K x U job through a bounded activation buffer
+ * without re-packing operand slabs. */
+int kws_sim_stem_range(const void* kwd_n, const void* utt_n, int C, int K, int U, int Tk, int Tu, int Dk,
+                       int pair_mode, int k0, int nk, int u0, int nu, const void* w_packed, const float* bias,
+                       int out_mode, void* out, void* stream);
 
 /* ---- scores ---------------------------------------------------------------- */
 

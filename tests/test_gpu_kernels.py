@@ -228,6 +228,26 @@ def test_sim_stem_fused_diag_and_many_items(ops, cuda_dev):
     assert maxerr(outd, refd) <= 3e-4 * max(1.0, refd.abs().max().item())
 
 
+def test_sim_stem_range_is_a_block_of_the_full_job(ops, cuda_dev):
+    """kws_sim_stem_range over keywords [k0,k1) x utterances [u0,u1) == that block of the full K x U job,
+    bit for bit (same kernel, same operands), written at the front of a larger reused buffer."""
+    g = gen(cuda_dev)
+    Cc, K, U, Tk, Tu, Dk = 6, 7, 5, 20, 130, 64
+    kn = unit_rows(Cc, K, Tk, Dk, g=g, dev=cuda_dev).half()
+    un = unit_rows(Cc, U, Tu, Dk, g=g, dev=cuda_dev).half()
+    sd = {k: v.to(cuda_dev) for k, v in O.make_weights("L", Cc, 64, seed=5).items()}
+    wp, bias = pack_stem(ops, sd)
+    full = ops.sim_stem(kn, un, wp, bias, ops.STEM_OUT_NCHW_F32)  # [K*U,64,Ho,Wo]
+    full = full.view(K, U, *full.shape[1:])
+    buf = torch.full((K * U * full[0, 0].numel(),), float("nan"), device=cuda_dev)
+    for (k0, k1, u0, u1) in [(2, 6, 1, 4), (0, 1, 4, 5), (6, 7, 0, 5)]:
+        blk = ops.sim_stem(kn, un, wp, bias, ops.STEM_OUT_NCHW_F32, out=buf, k_range=(k0, k1), u_range=(u0, u1))
+        assert blk.shape[0] == (k1 - k0) * (u1 - u0)
+        assert torch.equal(blk.view(k1 - k0, u1 - u0, *blk.shape[1:]), full[k0:k1, u0:u1])
+    with pytest.raises(Exception):
+        ops.sim_stem(kn, un, wp, bias, ops.STEM_OUT_NCHW_F32, k_range=(5, 9))
+
+
 # ---- scores + top-k -------------------------------------------------------------------------------
 def test_scores_and_detections(ops, cuda_dev):
     g = gen(cuda_dev)
