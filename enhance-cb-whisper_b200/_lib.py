@@ -12,7 +12,7 @@ import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libkws_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # constants of include/kws_b200.h
 F16, BF16 = 0, 1
@@ -29,6 +29,8 @@ SIGNATURES = {
     "kws_sm_count": (_i, []),
     "kws_pack_stem_weights": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp]),
     "kws_stem_weight_bytes": (_sz, [_i]),
+    "kws_pack_stem_fused": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp]),
+    "kws_stem_fused_weight_bytes": (_sz, [_i]),
     "kws_fold_temporal_weights": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _vp, _vp, _vp]),
     "kws_cast_f32_to_16": (_i, [_vp, _vp, _sz, _i, _vp]),
     "kws_normalize_rows": (_i, [_vp, _i, _i, _i, _i, C.POINTER(C.c_int32), _i, _vp, _f, _vp, _vp]),

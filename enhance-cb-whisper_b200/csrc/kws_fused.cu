@@ -1,69 +1,94 @@
 // Fused similarity + ResNet-stem kernel (sm_100a): the layer-wise cosine-similarity 'image'
 // of a (keyword, utterance) pair is produced tile by tile in tensor memory, converted to fp16
 // straight into the shared-memory operand layout of the stem convolution, and consumed there by
-// the tap-decomposed tcgen05 implicit GEMM.  The [pairs, C, Tk, Tu] tensor of the reference
+// a tap-decomposed tcgen05 implicit GEMM.  The [pairs, C, Tk, Tu] tensor of the reference
 // (model.py:174-191) never exists in HBM.
 //
 //   S_c[i, j]          = < kwd_n[c, k, i, :], utt_n[c, u, j, :] >                 (model.py:210-218)
 //   out[oc, oi, oj]    = relu(bias[oc] + sum_{c,di,dj} W'[oc,c,di,dj] S_c[2oi+di-3, 2oj+dj-3])
 //                                                        (HF modeling_resnet.py:39-54, BN folded)
 //
-// Work item = (pair, column tile of 61 output columns); an item walks down the image in steps of
-// two output rows.  One stem MMA covers M = 128 = 2 output rows x 64 pixel slots (61 used),
-// N = 64 output channels, K = 16 input channels, for one tap (di, dj); 49 taps accumulate in TMEM.
+// Work item = (pair, column tile of 60 output columns); an item walks down the image in steps of
+// two output rows (M = 128 = 2 output rows x 64 pixel slots, 60 used).
+//
+// An SS-mode tcgen05.mma is paced by shared-memory operand bytes (measured: max(M*N/256,
+// (bytes A + bytes B)/128) cycles, tools/umma_probe2.cu), so the stem is arranged to read the pixel
+// operand as rarely as possible:
+//   * N = 128: one MMA applies TWO taps to one read of the pixel operand.  Columns 0..63 of the
+//     accumulator ("half a") take tap dj, columns 64..127 ("half b") take tap dj+4 of the same input
+//     pixels; half b is therefore the partial sum of the output pixel two slots to the LEFT, and the
+//     epilogue adds D_a[x] + D_b[x+2] (warp shuffle).
+//   * K = 16 = two 8-element chunks whose distance (the descriptor's leading byte offset) is free:
+//     16 bytes = "the same rows one pixel further" (tap dj+2), or the distance to the other
+//     column-parity plane.
+//   * channels 8..11 of a pixel share a 16-byte chunk with channels 8..11 of its right neighbour in
+//     the same plane ("Y' chunk"), so 12 layers cost 1.5 chunks per tap instead of 2.
+//   Per kernel row di the 7 taps x 12 channels become 3 MMAs (2 for C <= 8) instead of 7:
+//     (X plane0 | X plane0 + 1 px)  a: dj 0, 2   b: dj 4, 6      channels 0..7
+//     (Y' plane0 | Y' plane1)       a: dj 0,2 | 1,3   b: dj 4,6 | 5,-   channels 8..11
+//     (X plane1 | X plane1 + 1 px)  a: dj 1, 3   b: dj 5, -      channels 0..7
 //
 // Shared-memory operand of the stem ("ring"): input rows are kept de-interleaved by column
-// parity (plane) and by row parity (rp), channels innermost in chunks of 8:
-//   block[k8][rp][plane] : ring of NR row slots x (64 pixels x 16 B)
-// For tap (di, dj) the 128 A-rows are 128 consecutive 16-byte pixels starting at
-//   slot(r0) * 1024 + (dj >> 1) * 16      in block[.][(di+1)&1][dj&1],   r0 = 4P + di - 3:
-// rows 0..63 read input row r0 (output row 2P), rows 64..127 run on into the next slot, which
-// holds input row r0 + 2 (output row 2P+1).  A tap only changes the descriptor start address.
+// parity (plane) and by row parity (rp), in blocks [k8 (X, Y')][rp][plane] of NR row slots x
+// (64 pixels x 16 B).  For kernel row di the 128 A-rows are 128 consecutive 16-byte pixels starting
+// at slot(r0) * 1024 (+16 per pixel of shift), r0 = 4P + di - 3: rows 0..63 read input row r0 (output
+// row 2P), rows 64..127 run on into the next slot, which holds input row r0 + 2 (output row 2P+1).
 // Slot NR mirrors slot 0 so the run never wraps.
 //
 // The similarity GEMM works on chunks of 16 input rows: for each layer c, D[128 px, 16 rows] =
-// utt tile (128 x Dk, TMA, OOB columns zero-filled) x kwd rows (16 x Dk)^T, fp32 in one of two
-// TMEM regions; 4 converter warps (thread = pixel) read 4 rows x C layers at a time, pack fp16
-// and store 16-byte (8-channel) words into the ring, one quantum (4 rows) per stem step.
+// utt tile (128 x Dk, TMA, OOB columns zero-filled = the conv's zero padding) x kwd rows (16 x Dk)^T,
+// fp32 in TMEM; 4 converter warps (thread = pixel) read 4 rows x C layers at a time, pack fp16 and
+// store into the ring, one quantum (4 rows) per stem step.
 //
-// Roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer (similarity + stem, similarity
-// stages are issued opportunistically between tap groups so the tensor pipe never waits on
-// them), warp 2 TMEM allocator, warps 4..7 stem epilogue, warps 8..11 converters.
+// TMEM: stem accumulators [0,128) and [128,256) (double-buffered), similarity region [256, 256+16C).
+// Roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer (one elected thread; similarity stages
+// are slipped between the stem's kernel rows), warp 2 TMEM allocator, warps 4..7 stem epilogue,
+// warps 8..11 converters.
 #include "kws_common.cuh"
 #include "../../include/kws_b200.h"
 
+// cycle counters of the roles (development aid): compiled in only with -DKWS_FUSED_TIMERS, they cost registers
+#ifdef KWS_FUSED_TIMERS
+#define KWS_CLK() clock64()
+#else
+#define KWS_CLK() 0ll
+#endif
+
 namespace kws {
 
-constexpr int F_THREADS = 384;
-constexpr int F_OC = 64;
-constexpr int F_TILE_OJ = 61;                      // output columns per item (2*61 + 5 = 127 <= 128 input px)
-constexpr int F_NR = 8;                            // ring slots per block = 4 quanta of 2 slots
-constexpr int F_BLOCK = (F_NR + 1) * 1024 + 64;    // 9280: +mirror slot, +64 keeps plane 1 on other banks
-constexpr int F_RING_BYTES = 8 * F_BLOCK;          // [k8 2][rp 2][plane 2]
-constexpr int F_TAP_BYTES = 2 * F_OC * 16;         // 2048: [k8][oc][8 ch] fp16
-constexpr int F_W_BYTES = 49 * F_TAP_BYTES;        // 100352
-constexpr int F_NS = 3;                            // similarity operand stages
-constexpr int F_A_BYTES = 128 * 128;               // utt tile 128 px x 64 dims (SW128)
-constexpr int F_B_BYTES = 16 * 128;                // kwd tile 16 rows x 64 dims (SW128)
-constexpr int F_STAGE = F_A_BYTES + F_B_BYTES;     // 18432
-constexpr int F_MAX_C = 12;
-constexpr int F_SIM_COLS = F_MAX_C * 16;           // 192 TMEM columns per similarity region
-constexpr int F_TMEM_SIM = 2 * F_OC;               // stem accumulators in columns [0,128)
-constexpr int F_NBAR = 2 * F_NS + 2 + 2 + 4 + 4 + 2 + 2;
+constexpr int G_THREADS = 384;
+constexpr int G_OC = 64;
+constexpr int G_TILE_OJ = 60;                      // output columns per item (2*59 + 6 = 124 <= 127 input px); slots 60..63 idle
+constexpr int G_NR = 8;                            // ring slots per block = 4 quanta of 2 slots
+constexpr int G_BLOCK = (G_NR + 1) * 1024 + 64;    // 9280: +mirror slot, +64 keeps plane 1 on other banks
+constexpr int G_RING_BYTES = 8 * G_BLOCK;          // [k8 2][rp 2][plane 2]
+constexpr int G_MMA_W_BYTES = 2 * 128 * 16;        // 4096: one MMA's B operand [chunk 2][n 128][8 ch] fp16
+constexpr int G_MAX_MMA = 3;                       // stem MMAs per kernel row
+constexpr int G_W_BYTES = 7 * G_MAX_MMA * G_MMA_W_BYTES;  // 86016
+constexpr int G_NS = 3;                            // similarity operand stages
+constexpr int G_A_BYTES = 128 * 128;               // utt tile 128 px x 64 dims (SW128)
+constexpr int G_B_BYTES = 16 * 128;                // kwd tile 16 rows x 64 dims (SW128)
+constexpr int G_STAGE = G_A_BYTES + G_B_BYTES;     // 18432
+constexpr int G_MAX_C = 12;
+constexpr int G_ACC_COLS = 128;                    // one stem accumulator: half a | half b
+constexpr int G_TMEM_SIM = 2 * G_ACC_COLS;         // similarity region starts at column 256
+constexpr int G_OUT_STAGE = 4 * 32 * 128;          // per epilogue warp: 32 pixels x 64 bf16 (SW128), source of its TMA stores
+constexpr int G_NBAR = 2 * G_NS + 1 + 1 + 4 + 4 + 2 + 2;
 
 struct FusedParams {
-  const uint4* w;     // packed stem weights (kws_pack_stem_weights, one 16-channel group)
+  const uint4* w;     // fused stem weights (kws_pack_stem_fused)
   const float* bias;  // [64]
   void* out;
   int out_mode;
   int C, K, U, Tk, Tu, nkb, Ho, Wo, col_tiles;  // K, U: operand batch sizes (tensor-map extents)
   int k0, u0, nk, nu;  // scored sub-range: keywords [k0, k0+nk) x utterances [u0, u0+nu); out pair = (k-k0)*nu + (u-u0)
+  int n_mma;     // stem MMAs per kernel row: 2 (C <= 8) or 3
   int nP;        // stem steps per item = ceil(Ho / 2)
   int nQ;        // quanta (4 input rows) converted per item = nP + 2
   int n_chunks;  // similarity chunks (16 input rows) per item = ceil(nQ / 4)
   int diag;
   long long num_items;
-  long long* dbg;  // optional [grid][8] cycle counters of the MMA issuer (development aid), or null
+  long long* dbg;  // optional [grid][16] cycle counters (issuer 0-4, epilogue 5-7, converter 8-11; development aid), or null
 };
 
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
@@ -78,6 +103,28 @@ __device__ __forceinline__ bool mbar_poll(uint64_t* bar, uint32_t parity, bool b
   if (!blocking) return false;
   mbar_wait(bar, parity, tag);
   return true;
+}
+
+// packed fp32x2 add (sm_100) and fused convert + ReLU: 3 instructions per two outputs in the bf16 epilogue
+__device__ __forceinline__ uint64_t pack_b64(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t relu_bf16x2(uint64_t v) {  // {lo, hi} fp32 -> bf16x2 (lo in the low half), max(., 0)
+  uint32_t lo, hi, r;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  return r;
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 struct ItemCoord {
@@ -98,43 +145,61 @@ __device__ __forceinline__ ItemCoord decode_item(const FusedParams& p, long long
   return r;
 }
 
-__global__ void __launch_bounds__(F_THREADS, 1)
+template <bool NHWC>  // NHWC: bf16 channels-last through TMA stores; else fp32 NCHW with direct stores (parity)
+__global__ void __launch_bounds__(G_THREADS, 1)
 kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_constant__ CUtensorMap map_kwd,
+                 const __grid_constant__ CUtensorMap map_out_lo, const __grid_constant__ CUtensorMap map_out_hi,
                  const FusedParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* s_ops = base;                          // F_NS * F_STAGE (each 1024-aligned)
-  uint8_t* s_w = s_ops + F_NS * F_STAGE;          // F_W_BYTES
-  uint8_t* s_ring = s_w + F_W_BYTES;              // F_RING_BYTES
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + F_RING_BYTES);
-  uint64_t* ofull = bars;                 // [F_NS] TMA -> MMA (similarity operands)
-  uint64_t* oempty = ofull + F_NS;        // [F_NS] MMA commit -> TMA
-  uint64_t* sfull = oempty + F_NS;        // [2] MMA commit -> converters (similarity region ready)
-  uint64_t* sempty = sfull + 2;           // [2] converters -> MMA
-  uint64_t* qfull = sempty + 2;           // [4] converters -> MMA (ring quantum written)
+  uint8_t* base = smem_raw;  // no alignment slack to spare: the declared 1024-byte alignment is checked below
+  uint8_t* s_ops = base;                          // G_NS * G_STAGE (each 1024-aligned)
+  uint8_t* s_w = s_ops + G_NS * G_STAGE;          // G_W_BYTES
+  uint8_t* s_ostage = s_w + G_W_BYTES;            // G_OUT_STAGE (4 x 4 KB, each 1024-aligned)
+  uint8_t* s_ring = s_ostage + G_OUT_STAGE;       // G_RING_BYTES
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + G_RING_BYTES);
+  uint64_t* ofull = bars;                 // [G_NS] TMA -> MMA (similarity operands)
+  uint64_t* oempty = ofull + G_NS;        // [G_NS] MMA commit -> TMA
+  uint64_t* sfull = oempty + G_NS;        // [1] MMA commit -> converters (similarity region ready)
+  uint64_t* sempty = sfull + 1;           // [1] converters -> MMA
+  uint64_t* qfull = sempty + 1;           // [4] converters -> MMA (ring quantum written)
   uint64_t* qempty = qfull + 4;           // [4] MMA commit -> converters
   uint64_t* afull = qempty + 4;           // [2] MMA commit -> epilogue (stem accumulator ready)
   uint64_t* aempty = afull + 2;           // [2] epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + F_NBAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + G_NBAR);
+  float* s_bias = reinterpret_cast<float*>(bars + G_NBAR + 2);  // [64]; L1 is carved down to nothing, keep it out of L2
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  for (int i = threadIdx.x; i < F_W_BYTES / 16; i += F_THREADS) reinterpret_cast<uint4*>(s_w)[i] = p.w[i];
+  {
+    const int w16 = 7 * p.n_mma * (G_MMA_W_BYTES / 16);
+    for (int i = threadIdx.x; i < w16; i += G_THREADS) reinterpret_cast<uint4*>(s_w)[i] = p.w[i];
+    // the ring is zeroed once: chunks nobody writes (Y' of the last pixel, unused planes for C <= 8) must hold
+    // finite values, they only ever meet zero weights or discarded pixel slots
+    for (int i = threadIdx.x; i < G_RING_BYTES / 16; i += G_THREADS)
+      reinterpret_cast<uint4*>(s_ring)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (threadIdx.x < G_OC) s_bias[threadIdx.x] = __ldg(p.bias + threadIdx.x);
+    if ((smem_u32(smem_raw) & 1023u) != 0) {
+      if (threadIdx.x == 0) printf("[kws] dynamic shared memory base 0x%x is not 1024-byte aligned\n", smem_u32(smem_raw));
+      __trap();
+    }
+  }
   fence_proxy_async();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_utt);
     tma_prefetch_desc(&map_kwd);
+    tma_prefetch_desc(&map_out_lo);
+    tma_prefetch_desc(&map_out_hi);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < F_NS; ++s) {
+    for (int s = 0; s < G_NS; ++s) {
       mbar_init(&ofull[s], 1);
       mbar_init(&oempty[s], 1);
     }
+    mbar_init(&sfull[0], 1);
+    mbar_init(&sempty[0], 128);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&sfull[s], 1);
-      mbar_init(&sempty[s], 128);
       mbar_init(&afull[s], 1);
       mbar_init(&aempty[s], 128);
     }
@@ -165,229 +230,386 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
       uint32_t phase = 0;
       for (long long it = blockIdx.x; it < p.num_items; it += gridDim.x) {
         const ItemCoord w = decode_item(p, it);
-        const int jbase = 2 * F_TILE_OJ * w.ct - 3;  // input column of pixel x = 0 (OOB columns read as zero)
+        const int jbase = 2 * G_TILE_OJ * w.ct - 3;  // input column of pixel x = 0 (OOB columns read as zero)
         for (int n = 0; n < p.n_chunks; ++n) {
           for (int c = 0; c < p.C; ++c) {
             for (int kb = 0; kb < p.nkb; ++kb) {
               mbar_wait(&oempty[stage], phase ^ 1, 100 + stage);
-              uint8_t* sa = s_ops + stage * F_STAGE;
-              mbar_arrive_expect_tx(&ofull[stage], F_STAGE);
+              uint8_t* sa = s_ops + stage * G_STAGE;
+              mbar_arrive_expect_tx(&ofull[stage], G_STAGE);
               tma_load_3d(&map_utt, &ofull[stage], sa, kb * 64, jbase, c * p.U + w.u);
-              tma_load_3d(&map_kwd, &ofull[stage], sa + F_A_BYTES, kb * 64, 16 * n - 3, c * p.K + w.kw);
-              if (++stage == F_NS) stage = 0, phase ^= 1;
+              tma_load_3d(&map_kwd, &ofull[stage], sa + G_A_BYTES, kb * 64, 16 * n - 3, c * p.K + w.kw);
+              if (++stage == G_NS) stage = 0, phase ^= 1;
             }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    // The whole warp runs this loop with identical (warp-uniform) values; only lane 0 executes the
-    // tcgen05 instructions (predicated inside the asm), so descriptor arithmetic stays in uniform
-    // registers and one MMA costs a handful of issue slots.
+    // ===================== MMA issuer (one elected thread) =====================
     if (elect_one()) {
-    const uint32_t idesc_sim = make_idesc_f16(128, 16, 0);
-    const uint32_t idesc_stem = make_idesc_f16(128, F_OC, 0);
-    const uint32_t ops_u32 = smem_u32(s_ops);
-    const uint64_t adesc0 = make_smem_desc(smem_u32(s_ring), 4 * F_BLOCK, 128, LAYOUT_NONE);
-    const uint64_t bdesc0 = make_smem_desc(smem_u32(s_w), F_OC * 16, 128, LAYOUT_NONE);
-    const uint64_t sdesc0 = make_smem_desc(0, 16, 1024, LAYOUT_SW128);
-    // similarity cursor: runs ahead of the stem cursor (across items) by about one chunk
-    long long s_it = blockIdx.x;
-    int s_chunk = 0, s_stage = 0;
-    uint32_t s_g = 0;  // similarity chunks fully issued so far (global)
-    int o_stage = 0;
-    uint32_t o_phase = 0;
-    // one operand stage = 4 MMAs of one layer / k-block; non-blocking calls return false when the
-    // TMEM region or the operands are not there yet (the stem MMAs go on, the call is retried)
-    auto sim_issue = [&](bool blocking) -> bool {
-      const uint32_t buf = s_g & 1;
-      if (s_stage == 0 && !mbar_poll(&sempty[buf], ((s_g >> 1) & 1) ^ 1, blocking, 500 + buf)) return false;
-      if (!mbar_poll(&ofull[o_stage], o_phase, blocking, 300 + o_stage)) return false;
-      tc_fence_after();
-      const int c = s_stage / p.nkb, kb = s_stage - c * p.nkb;
-      const uint32_t d = F_TMEM_SIM + buf * F_SIM_COLS + c * 16;  // TMEM base is 0 (checked at start)
-      const uint32_t sa = ops_u32 + o_stage * F_STAGE;
-      const uint64_t adesc = sdesc0 + (uint64_t)(sa >> 4);
-      const uint64_t bdesc = adesc + (uint64_t)(F_A_BYTES >> 4);
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_f16(d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc_sim, (kb | k) != 0);
-      umma_commit(&oempty[o_stage]);
-      if (++o_stage == F_NS) o_stage = 0, o_phase ^= 1;
-      if (++s_stage == stages_per_chunk) {
-        umma_commit(&sfull[buf]);
-        s_stage = 0;
-        ++s_g;
-        if (++s_chunk == p.n_chunks) s_chunk = 0, s_it += gridDim.x;
-      }
-      return true;
-    };
-
-    uint32_t g_chunk0 = 0;  // global index of the current item's chunk 0
-    uint32_t qbase = 0;     // global index of the current item's quantum 0
-    uint32_t acc_seq = 0;   // global stem step counter -> accumulator buffer
-    long long tm_sim = 0, tm_acc = 0, tm_q = 0, tm_issue = 0;
-    const long long tm_start = clock64();
-    for (long long it = blockIdx.x; it < p.num_items; it += gridDim.x) {
-      int waited = 0;  // quanta of this item known to be in the ring
-      for (int P = 0; P < p.nP; ++P, ++acc_seq) {
-        // chunks: `need` holds quantum P+2 and must be issued now; `ahead` (one chunk further,
-        // possibly chunk 0 of the next item) is issued one stage per tap group while the stem runs
-        int need = (P + 2) >> 2;
-        if (need > p.n_chunks - 1) need = p.n_chunks - 1;
-        int ahead = ((P + 2) >> 2) + 1;
-        if (ahead > p.n_chunks) ahead = p.n_chunks;
-        const uint32_t g_need = g_chunk0 + (uint32_t)need, g_ahead = g_chunk0 + (uint32_t)ahead;
-        const long long t0 = clock64();
-        while (s_g <= g_need && s_it < p.num_items) sim_issue(true);
-        const long long t1 = clock64();
-        const uint32_t acc = acc_seq & 1;
-        mbar_wait(&aempty[acc], ((acc_seq >> 1) & 1) ^ 1, 200 + acc);
-        const long long t2 = clock64();
-        while (waited <= P + 2 && waited < p.nQ) {
-          const uint32_t G = qbase + waited;
-          mbar_wait(&qfull[G & 3], (G >> 2) & 1, 400 + (int)(G & 3));
-          ++waited;
-        }
-        const long long t3 = clock64();
-        tm_sim += t1 - t0, tm_acc += t2 - t1, tm_q += t3 - t2;
+      const uint32_t idesc_sim = make_idesc_f16(128, 16, 0);
+      const uint32_t idesc_stem = make_idesc_f16(128, 2 * G_OC, 0);
+      const uint32_t ops_u32 = smem_u32(s_ops);
+      // A descriptors: SBO = 128 (8 pixels x 16 B); LBO = distance between the two 8-element K chunks
+      const uint64_t adesc_px = make_smem_desc(smem_u32(s_ring), 16, 128, LAYOUT_NONE);        // +1 pixel
+      const uint64_t adesc_pl = make_smem_desc(smem_u32(s_ring), G_BLOCK, 128, LAYOUT_NONE);   // other plane
+      const uint64_t bdesc0 = make_smem_desc(smem_u32(s_w), 128 * 16, 128, LAYOUT_NONE);
+      const uint64_t sdesc0 = make_smem_desc(0, 16, 1024, LAYOUT_SW128);
+      const int n_mma = p.n_mma;
+      // similarity cursor: runs ahead of the stem cursor (across items)
+      long long s_it = blockIdx.x;
+      int s_chunk = 0, s_stage = 0;
+      uint32_t s_g = 0;  // similarity chunks fully issued so far (global)
+      int o_stage = 0;
+      uint32_t o_phase = 0;
+      // one operand stage = 4 MMAs of one layer / k-block; non-blocking calls return false when the
+      // TMEM region or the operands are not there yet (the stem MMAs go on, the call is retried)
+      auto sim_issue = [&](bool blocking) -> bool {
+        if (s_stage == 0 && !mbar_poll(&sempty[0], (s_g & 1) ^ 1, blocking, 500)) return false;
+        if (!mbar_poll(&ofull[o_stage], o_phase, blocking, 300 + o_stage)) return false;
         tc_fence_after();
-        const uint32_t d = acc * F_OC;
-        const uint32_t slot_base = 2 * (qbase + P);
+        const int c = s_stage / p.nkb, kb = s_stage - c * p.nkb;
+        const uint32_t d = G_TMEM_SIM + c * 16;  // TMEM base is 0 (checked at start)
+        const uint32_t sa = ops_u32 + o_stage * G_STAGE;
+        const uint64_t adesc = sdesc0 + (uint64_t)(sa >> 4);
+        const uint64_t bdesc = adesc + (uint64_t)(G_A_BYTES >> 4);
 #pragma unroll
-        for (int di = 0; di < 7; ++di) {
-          const uint32_t slot0 = (slot_base + (di >> 1)) & (F_NR - 1);
-          const uint64_t a_row = adesc0 + (uint64_t)(((((di + 1) & 1) * 2 * F_BLOCK) >> 4) + slot0 * 64);
-          const uint64_t b_row = bdesc0 + (uint64_t)((di * 7 * F_TAP_BYTES) >> 4);
-#pragma unroll
-          for (int dj = 0; dj < 7; ++dj) {
-            umma_f16(d, a_row + (uint64_t)((((dj & 1) * F_BLOCK) + (dj >> 1) * 16) >> 4),
-                       b_row + (uint64_t)((dj * F_TAP_BYTES) >> 4), idesc_stem, (di | dj) != 0);
-          }
-          if (s_g <= g_ahead && s_it < p.num_items) sim_issue(false);
+        for (int k = 0; k < 4; ++k)
+          umma_f16(d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc_sim, (kb | k) != 0);
+        umma_commit(&oempty[o_stage]);
+        if (++o_stage == G_NS) o_stage = 0, o_phase ^= 1;
+        if (++s_stage == stages_per_chunk) {
+          umma_commit(&sfull[0]);
+          s_stage = 0;
+          ++s_g;
+          if (++s_chunk == p.n_chunks) s_chunk = 0, s_it += gridDim.x;
         }
-        umma_commit(&qempty[(qbase + P) & 3]);  // quantum P is dead once these MMAs retire
-        umma_commit(&afull[acc]);
-        tm_issue += clock64() - t3;
+        return true;
+      };
+
+      uint32_t g_chunk0 = 0;  // global index of the current item's chunk 0
+      uint32_t qbase = 0;     // global index of the current item's quantum 0
+      uint32_t acc_seq = 0;   // global stem step counter -> accumulator buffer
+      long long tm_sim = 0, tm_acc = 0, tm_q = 0, tm_issue = 0;
+      const long long tm_start = KWS_CLK();
+      for (long long it = blockIdx.x; it < p.num_items; it += gridDim.x) {
+        int waited = 0;  // quanta of this item known to be in the ring
+        for (int P = 0; P < p.nP; ++P, ++acc_seq) {
+          // chunks: `need` holds quantum P+2 and must be issued now; `ahead` (one chunk further,
+          // possibly chunk 0 of the next item) is issued a stage at a time while the stem runs
+          int need = (P + 2) >> 2;
+          if (need > p.n_chunks - 1) need = p.n_chunks - 1;
+          int ahead = ((P + 2) >> 2) + 1;
+          if (ahead > p.n_chunks) ahead = p.n_chunks;
+          const uint32_t g_need = g_chunk0 + (uint32_t)need, g_ahead = g_chunk0 + (uint32_t)ahead;
+          const uint32_t acc = acc_seq & 1;
+          const long long t1 = KWS_CLK();
+          mbar_wait(&aempty[acc], ((acc_seq >> 1) & 1) ^ 1, 200 + acc);
+          const long long t2 = KWS_CLK();
+          // kernel rows 0..5 read quanta P and P+1 only; quantum P+2 (input row 4P+5) is first touched by di = 6.
+          // A quantum may only be waited for once its similarity chunk has been issued (else: deadlock).
+          {
+            int c1 = (P + 1) >> 2;
+            if (c1 > p.n_chunks - 1) c1 = p.n_chunks - 1;
+            while (s_g <= g_chunk0 + (uint32_t)c1 && s_it < p.num_items) sim_issue(true);
+          }
+          while (waited <= P + 1 && waited < p.nQ) {
+            const uint32_t G = qbase + waited;
+            mbar_wait(&qfull[G & 3], (G >> 2) & 1, 400 + (int)(G & 3));
+            ++waited;
+          }
+          const long long t3 = KWS_CLK();
+          tm_acc += t2 - t1, tm_q += t3 - t2;
+          tc_fence_after();
+          const uint32_t d = acc * G_ACC_COLS;
+          const uint32_t slot_base = 2 * (qbase + P);
+#pragma unroll
+          for (int di = 0; di < 7; ++di) {
+            if (di == 6) {
+              // the chunk holding quantum P+2 must have been issued before we may block on that quantum
+              const long long u0 = KWS_CLK();
+              while (s_g <= g_need && s_it < p.num_items) sim_issue(true);
+              const long long u1 = KWS_CLK();
+              while (waited <= P + 2 && waited < p.nQ) {
+                const uint32_t G = qbase + waited;
+                mbar_wait(&qfull[G & 3], (G >> 2) & 1, 400 + (int)(G & 3));
+                ++waited;
+              }
+              tm_sim += u1 - u0, tm_q += KWS_CLK() - u1;
+              tc_fence_after();
+            }
+            const uint32_t slot0 = (slot_base + (di >> 1)) & (G_NR - 1);
+            // block [k8][rp][plane]: rp = (di+1)&1; byte offsets in 16-byte units
+            const uint32_t row16 = ((((di + 1) & 1) * 2 * G_BLOCK) >> 4) + slot0 * 64;
+            const uint64_t b_row = bdesc0 + (uint64_t)((di * n_mma * G_MMA_W_BYTES) >> 4);
+            // (X plane0 | +1 px): half a taps 0,2; half b taps 4,6
+            umma_f16(d, adesc_px + (uint64_t)row16, b_row, idesc_stem, di != 0);
+            if (n_mma == 3) {
+              // (Y' plane0 | Y' plane1): channels 8..11 of all seven taps
+              umma_f16(d, adesc_pl + (uint64_t)(row16 + ((4 * G_BLOCK) >> 4)), b_row + (uint64_t)(G_MMA_W_BYTES >> 4),
+                       idesc_stem, 1);
+            }
+            // (X plane1 | +1 px): half a taps 1,3; half b tap 5
+            umma_f16(d, adesc_px + (uint64_t)(row16 + (G_BLOCK >> 4)),
+                     b_row + (uint64_t)(((n_mma - 1) * G_MMA_W_BYTES) >> 4), idesc_stem, 1);
+            // similarity stages of the next chunk(s) ride along, two per kernel row
+            if (s_g <= g_ahead && s_it < p.num_items) sim_issue(false);
+          }
+          umma_commit(&qempty[(qbase + P) & 3]);  // quantum P is dead once these MMAs retire
+          umma_commit(&afull[acc]);
+          tm_issue += KWS_CLK() - t3;
+        }
+        // the two tail quanta were read by the last step only
+        for (int q = p.nP; q < p.nQ; ++q) umma_commit(&qempty[(qbase + q) & 3]);
+        qbase += p.nQ;
+        g_chunk0 += p.n_chunks;
       }
-      // the two tail quanta were read by the last step only
-      for (int q = p.nP; q < p.nQ; ++q) umma_commit(&qempty[(qbase + q) & 3]);
-      qbase += p.nQ;
-      g_chunk0 += p.n_chunks;
-    }
-    if (p.dbg) {
-      long long* o = p.dbg + (size_t)blockIdx.x * 8;
-      o[0] = clock64() - tm_start, o[1] = tm_sim, o[2] = tm_acc, o[3] = tm_q, o[4] = tm_issue;
-    }
+      if (p.dbg) {
+        long long* o = p.dbg + (size_t)blockIdx.x * 32;
+        o[0] = KWS_CLK() - tm_start, o[1] = tm_sim, o[2] = tm_acc, o[3] = tm_q, o[4] = tm_issue;
+      }
     }
     __syncwarp();
   } else if (warp >= 4 && warp < 8) {
     // ===================== stem epilogue =====================
+    // lane of TMEM = pixel slot; out[x] = relu(D_a[x] + D_b[x+2] + bias) (half b belongs to the pixel two
+    // slots to the left).  bf16 channels-last results are staged per warp in shared memory (32 pixels x 128 B,
+    // 128B-swizzled) and leave through one TMA store per warp and step: full 128-byte lines, edges clipped
+    // by the tensor map.  The staging buffer doubles as the mailbox through which pixels 30, 31 of a row
+    // receive half b of pixels 32, 33 (lanes 0, 1 of the neighbouring warp).
     const int q = warp & 3;
     const int row_sel = q >> 1;
     const int ojl = (q & 1) * 32 + lane;
-    float bias_r[F_OC];
-#pragma unroll
-    for (int i = 0; i < F_OC; ++i) bias_r[i] = __ldg(p.bias + i);
+    const bool lo_warp = (q & 1) == 0;
+    constexpr bool nhwc = NHWC;
+    uint8_t* my_stage = s_ostage + q * (32 * 128);
+    // mailboxes (2 lanes x 32 fp32 per channel group) live in the hi warp's never-stored pixel rows 28..31
+    float* mbox0 = reinterpret_cast<float*>(s_ostage + (q | 1) * (32 * 128) + 28 * 128);
+    float* mbox1 = mbox0 + 64;
+    const CUtensorMap* my_map = lo_warp ? &map_out_lo : &map_out_hi;
     uint32_t acc_seq = 0;
+    long long te_wait = 0, te_ld = 0, te_rest = 0;
+    long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (long long it = blockIdx.x; it < p.num_items; it += gridDim.x) {
       const ItemCoord w = decode_item(p, it);
-      const int oj = w.ct * F_TILE_OJ + ojl;
-      const bool col_ok = ojl < F_TILE_OJ && oj < p.Wo;
+      const int oj = w.ct * G_TILE_OJ + ojl;
+      const bool col_ok = ojl < G_TILE_OJ && oj < p.Wo;
       for (int P = 0; P < p.nP; ++P, ++acc_seq) {
         const uint32_t acc = acc_seq & 1;
+        const long long e0 = KWS_CLK();
         mbar_wait(&afull[acc], (acc_seq >> 1) & 1, 600 + acc);
+        const long long e1 = KWS_CLK();
+        te_wait += e1 - e0;
         tc_fence_after();
-        const uint32_t t_row = tmem_base + acc * F_OC + ((uint32_t)(q * 32) << 16);
-        uint32_t v[4][16];
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) tmem_ld16(t_row + ch * 16, v[ch]);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(&aempty[acc]);
+        const uint32_t t_row = tmem_base + acc * G_ACC_COLS + ((uint32_t)(q * 32) << 16);
         const int oi = 2 * P + row_sel;
-        if (col_ok && oi < p.Ho) {
-          if (p.out_mode == KWS_STEM_OUT_NCHW_F32) {
-            float* o = reinterpret_cast<float*>(p.out) + ((w.pair * F_OC) * p.Ho + oi) * (long long)p.Wo + oj;
-            const long long oc_stride = (long long)p.Ho * p.Wo;
+        const bool ok = col_ok && oi < p.Ho;
+        float* o32 = nullptr;
+        long long oc_stride = 0;
+        if (!nhwc) {
+          o32 = reinterpret_cast<float*>(p.out) + ((w.pair * G_OC) * p.Ho + oi) * (long long)p.Wo + oj;
+          oc_stride = (long long)p.Ho * p.Wo;
+        }
+        uint8_t* srow = my_stage + lane * 128;
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch)
+        for (int grp = 0; grp < 2; ++grp) {  // 32 output channels per TMEM round trip
+          uint32_t va[2][16], vb[2][16];
 #pragma unroll
-              for (int e = 0; e < 16; ++e)
-                o[(ch * 16 + e) * oc_stride] = fmaxf(__uint_as_float(v[ch][e]) + bias_r[ch * 16 + e], 0.f);
-          } else {
-            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) +
-                                                ((w.pair * p.Ho + oi) * (long long)p.Wo + oj) * F_OC);
+          for (int h = 0; h < 2; ++h) {
+            tmem_ld16(t_row + G_OC + grp * 32 + h * 16, vb[h]);
+            tmem_ld16(t_row + grp * 32 + h * 16, va[h]);
+          }
+          if (grp == 0) {
+            // the previous step's TMA store must have read this warp's staging buffer before it is reused
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+          }
+          tmem_ld_wait();
+          const long long f0 = KWS_CLK();
+          if (grp == 1) {  // last TMEM read of this accumulator
+            tc_fence_before();
+            mbar_arrive(&aempty[acc]);
+            te_ld += KWS_CLK() - e1;
+          }
+          float* mbox = grp == 0 ? mbox0 : mbox1;
+          if (!lo_warp && lane < 2) {
+            float4* dst = reinterpret_cast<float4*>(mbox + lane * 32);
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-              uint32_t pk[8];
+            for (int h = 0; h < 2; ++h)
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float a = fmaxf(__uint_as_float(v[ch][2 * e]) + bias_r[ch * 16 + 2 * e], 0.f);
-                const float b = fmaxf(__uint_as_float(v[ch][2 * e + 1]) + bias_r[ch * 16 + 2 * e + 1], 0.f);
-                pk[e] = pack_bf162(a, b);
+              for (int e = 0; e < 16; e += 4)
+                dst[h * 4 + (e >> 2)] = make_float4(__uint_as_float(vb[h][e]), __uint_as_float(vb[h][e + 1]),
+                                                    __uint_as_float(vb[h][e + 2]), __uint_as_float(vb[h][e + 3]));
+          }
+          named_bar_sync(1 + row_sel, 64);  // mailbox written (and the other mailbox has been read)
+          const long long f1 = KWS_CLK();
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int e = 0; e < 16; ++e) vb[h][e] = __shfl_down_sync(0xffffffffu, vb[h][e], 2);
+          if (lo_warp && lane >= 30) {
+            const float4* src = reinterpret_cast<const float4*>(mbox + (lane - 30) * 32);
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+              for (int e = 0; e < 16; e += 4) {
+                const float4 f = src[h * 4 + (e >> 2)];
+                vb[h][e] = __float_as_uint(f.x), vb[h][e + 1] = __float_as_uint(f.y);
+                vb[h][e + 2] = __float_as_uint(f.z), vb[h][e + 3] = __float_as_uint(f.w);
               }
-              o[ch * 2] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              o[ch * 2 + 1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int ch = grp * 2 + h;
+            if constexpr (nhwc) {
+              uint32_t o[8];
+#pragma unroll
+              for (int e = 0; e < 16; e += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(s_bias + ch * 16 + e);
+                const uint64_t s0 = add_f32x2(add_f32x2(pack_b64(va[h][e], va[h][e + 1]), pack_b64(vb[h][e], vb[h][e + 1])),
+                                              pack_b64(__float_as_uint(b4.x), __float_as_uint(b4.y)));
+                const uint64_t s1 =
+                    add_f32x2(add_f32x2(pack_b64(va[h][e + 2], va[h][e + 3]), pack_b64(vb[h][e + 2], vb[h][e + 3])),
+                              pack_b64(__float_as_uint(b4.z), __float_as_uint(b4.w)));
+                o[e >> 1] = relu_bf16x2(s0);
+                o[(e >> 1) + 1] = relu_bf16x2(s1);
+              }
+              // 16-byte chunks 2ch, 2ch+1 of this pixel's 128-byte row, 128B swizzle (chunk ^ (row & 7));
+              // rows 28..31 of the hi warp are idle pixel slots and hold the mailboxes: never written here
+              if (lo_warp || lane < G_TILE_OJ - 32) {
+                *reinterpret_cast<uint4*>(srow + (((2 * ch) ^ (lane & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<uint4*>(srow + (((2 * ch + 1) ^ (lane & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+              }
+            } else {
+              float r[16];
+#pragma unroll
+              for (int e = 0; e < 16; e += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(s_bias + ch * 16 + e);
+                r[e] = fmaxf(__uint_as_float(va[h][e]) + __uint_as_float(vb[h][e]) + b4.x, 0.f);
+                r[e + 1] = fmaxf(__uint_as_float(va[h][e + 1]) + __uint_as_float(vb[h][e + 1]) + b4.y, 0.f);
+                r[e + 2] = fmaxf(__uint_as_float(va[h][e + 2]) + __uint_as_float(vb[h][e + 2]) + b4.z, 0.f);
+                r[e + 3] = fmaxf(__uint_as_float(va[h][e + 3]) + __uint_as_float(vb[h][e + 3]) + b4.w, 0.f);
+              }
+              if (ok) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) o32[(ch * 16 + e) * oc_stride] = r[e];
+              }
             }
+          }
+          const long long f2 = KWS_CLK();
+          tp[grp * 3 + 0] += f0 - (grp == 0 ? e1 : tp[7]);
+          tp[grp * 3 + 1] += f1 - f0;
+          tp[grp * 3 + 2] += f2 - f1;
+          tp[7] = f2;
+        }
+        if constexpr (nhwc) {
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && oi < p.Ho && w.ct * G_TILE_OJ + (q & 1) * 32 < p.Wo) {
+            asm volatile(
+                "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                    reinterpret_cast<uint64_t>(my_map)),
+                "r"(smem_u32(my_stage)), "r"(0), "r"(w.ct * G_TILE_OJ + (q & 1) * 32), "r"(oi), "r"((int)w.pair)
+                : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        te_rest += KWS_CLK() - e1;
+        tp[6] += KWS_CLK() - tp[7];
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all stores complete before exit
+    if (p.dbg && warp == 4 && lane == 0) {
+      long long* o = p.dbg + (size_t)blockIdx.x * 32;
+      o[5] = te_wait, o[6] = te_ld, o[7] = te_rest;
+      for (int i = 0; i < 7; ++i) o[16 + i] = tp[i];
+    }
+  } else if (warp >= 8) {
+    // ===================== converters: TMEM similarity rows -> fp16 ring =====================
+    // A whole chunk (4 quanta x 4 rows x C layers) is pulled out of TMEM and packed to fp16 registers as soon
+    // as its MMAs retire, so the single similarity region is handed back for the next chunk at once; the packed
+    // rows then enter the ring at the pace the stem frees slots.
+    const int q4 = warp & 3;
+    const int x = q4 * 32 + lane;  // pixel of the 128-wide input window
+    uint8_t* dst_px = s_ring + (x & 1) * G_BLOCK + (x >> 1) * 16;
+    const bool has_left = (x >> 1) > 0;  // Y' chunk of the left neighbour (same plane) takes our channels 8..11 too
+    const uint32_t t_lane = tmem_base + G_TMEM_SIM + ((uint32_t)(q4 * 32) << 16);
+    const bool yp = p.n_mma == 3;
+    uint32_t g = 0;   // global similarity chunk counter
+    uint32_t Gq = 0;  // global quantum counter
+    long long tc_sfull = 0, tc_qempty = 0, tc_ld = 0, tc_st = 0;
+    for (long long it = blockIdx.x; it < p.num_items; it += gridDim.x) {
+      for (int q0 = 0; q0 < p.nQ; q0 += 4, ++g) {
+        const int nq = p.nQ - q0 < 4 ? p.nQ - q0 : 4;
+        const long long c0 = KWS_CLK();
+        mbar_wait(&sfull[0], g & 1, 700);
+        tc_fence_after();
+        const long long c1 = KWS_CLK();
+        uint4 px[4][4];  // [quantum][row] channels 0..7
+        uint2 py[4][4];  // [quantum][row] channels 8..11
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          if (qq < nq) {
+            uint32_t v[G_MAX_C][4];
+#pragma unroll
+            for (int c = 0; c < G_MAX_C; ++c) {
+              if (c < p.C) {
+                tmem_ld4(t_lane + c * 16 + qq * 4, v[c]);
+              } else {
+                v[c][0] = v[c][1] = v[c][2] = v[c][3] = 0u;  // +0.0f
+              }
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              px[qq][t] = make_uint4(pack_half2(__uint_as_float(v[0][t]), __uint_as_float(v[1][t])),
+                                     pack_half2(__uint_as_float(v[2][t]), __uint_as_float(v[3][t])),
+                                     pack_half2(__uint_as_float(v[4][t]), __uint_as_float(v[5][t])),
+                                     pack_half2(__uint_as_float(v[6][t]), __uint_as_float(v[7][t])));
+              py[qq][t] = make_uint2(pack_half2(__uint_as_float(v[8][t]), __uint_as_float(v[9][t])),
+                                     pack_half2(__uint_as_float(v[10][t]), __uint_as_float(v[11][t])));
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&sempty[0]);  // the region may be refilled
+        const long long c2 = KWS_CLK();
+        tc_sfull += c1 - c0, tc_ld += c2 - c1;
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          if (qq < nq) {
+            const long long c3 = KWS_CLK();
+            mbar_wait(&qempty[Gq & 3], ((Gq >> 2) & 1) ^ 1, 800 + (int)(Gq & 3));
+            const long long c4 = KWS_CLK();
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              // input row r = 4q + t - 3: parity (t+1)&1, ring slot (2 Gq + (t >> 1)) mod NR
+              const uint32_t slot = (2 * Gq + (t >> 1)) & (G_NR - 1);
+              uint8_t* d0 = dst_px + ((t + 1) & 1) * 2 * G_BLOCK + slot * 1024;
+              *reinterpret_cast<uint4*>(d0) = px[qq][t];
+              if (slot == 0) *reinterpret_cast<uint4*>(d0 + G_NR * 1024) = px[qq][t];  // mirror: tap windows never wrap
+              if (yp) {
+                uint8_t* dy = d0 + 4 * G_BLOCK;
+                *reinterpret_cast<uint2*>(dy) = py[qq][t];                    // own chunk, elements 0..3
+                if (has_left) *reinterpret_cast<uint2*>(dy - 8) = py[qq][t];  // left neighbour's chunk, elements 4..7
+                if (slot == 0) {
+                  *reinterpret_cast<uint2*>(dy + G_NR * 1024) = py[qq][t];
+                  if (has_left) *reinterpret_cast<uint2*>(dy + G_NR * 1024 - 8) = py[qq][t];
+                }
+              }
+            }
+            fence_proxy_async();
+            mbar_arrive(&qfull[Gq & 3]);
+            ++Gq;
+            tc_qempty += c4 - c3, tc_st += KWS_CLK() - c4;
           }
         }
       }
     }
-  } else if (warp >= 8) {
-    // ===================== converters: TMEM similarity rows -> fp16 ring =====================
-    const int q4 = warp & 3;
-    const int x = q4 * 32 + lane;  // pixel of the 128-wide input window
-    uint8_t* dst_px = s_ring + (x & 1) * F_BLOCK + (x >> 1) * 16;
-    const uint32_t t_lane = tmem_base + F_TMEM_SIM + ((uint32_t)(q4 * 32) << 16);
-    uint32_t g = 0;   // global similarity chunk counter
-    uint32_t Gq = 0;  // global quantum counter
-    for (long long it = blockIdx.x; it < p.num_items; it += gridDim.x) {
-      for (int q = 0; q < p.nQ; ++q, ++Gq) {
-        const int qq = q & 3;
-        const uint32_t buf = g & 1;
-        if (qq == 0) {
-          mbar_wait(&sfull[buf], (g >> 1) & 1, 700 + buf);
-          tc_fence_after();
-        }
-        uint32_t v[F_MAX_C][4];
-#pragma unroll
-        for (int c = 0; c < F_MAX_C; ++c) {
-          if (c < p.C) {
-            tmem_ld4(t_lane + buf * F_SIM_COLS + c * 16 + qq * 4, v[c]);
-          } else {
-            v[c][0] = v[c][1] = v[c][2] = v[c][3] = 0u;  // +0.0f
-          }
-        }
-        tmem_ld_wait();
-        if (qq == 3 || q == p.nQ - 1) {  // last quantum read from this region
-          tc_fence_before();
-          mbar_arrive(&sempty[buf]);
-          ++g;
-        }
-        mbar_wait(&qempty[Gq & 3], ((Gq >> 2) & 1) ^ 1, 800 + (int)(Gq & 3));
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          // input row r = 4q + t - 3: parity (t+1)&1, ring slot (2 Gq + (t >> 1)) mod NR
-          const uint32_t slot = (2 * Gq + (t >> 1)) & (F_NR - 1);
-          uint8_t* d0 = dst_px + ((t + 1) & 1) * 2 * F_BLOCK + slot * 1024;
-          const uint4 lo = make_uint4(pack_half2(__uint_as_float(v[0][t]), __uint_as_float(v[1][t])),
-                                      pack_half2(__uint_as_float(v[2][t]), __uint_as_float(v[3][t])),
-                                      pack_half2(__uint_as_float(v[4][t]), __uint_as_float(v[5][t])),
-                                      pack_half2(__uint_as_float(v[6][t]), __uint_as_float(v[7][t])));
-          const uint4 hi = make_uint4(pack_half2(__uint_as_float(v[8][t]), __uint_as_float(v[9][t])),
-                                      pack_half2(__uint_as_float(v[10][t]), __uint_as_float(v[11][t])), 0u, 0u);
-          *reinterpret_cast<uint4*>(d0) = lo;
-          *reinterpret_cast<uint4*>(d0 + 4 * F_BLOCK) = hi;
-          if (slot == 0) {  // mirror of slot 0 after the last slot: tap windows never wrap
-            *reinterpret_cast<uint4*>(d0 + F_NR * 1024) = lo;
-            *reinterpret_cast<uint4*>(d0 + 4 * F_BLOCK + F_NR * 1024) = hi;
-          }
-        }
-        fence_proxy_async();
-        mbar_arrive(&qfull[Gq & 3]);
-      }
+    if (p.dbg && warp == 8 && lane == 0) {
+      long long* o = p.dbg + (size_t)blockIdx.x * 32;
+      o[8] = tc_sfull, o[9] = tc_ld, o[10] = tc_qempty, o[11] = tc_st;
     }
   }
 
@@ -399,43 +621,91 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
   }
 }
 
-constexpr size_t F_SMEM = 1024 + (size_t)F_NS * F_STAGE + F_W_BYTES + F_RING_BYTES + F_NBAR * 8 + 16;
-static_assert(F_SMEM <= 232448, "fused kernel exceeds the 227 KB shared-memory limit");
+constexpr size_t G_SMEM = (size_t)G_NS * G_STAGE + G_W_BYTES + G_OUT_STAGE + G_RING_BYTES + G_NBAR * 8 + 16 + G_OC * 4;
+static_assert(G_SMEM <= 232448, "fused kernel exceeds the 227 KB shared-memory limit");
+
+// Fused-kernel weight layout: [di 7][m n_mma][chunk 2][n 128][e 8] fp16, BN scale folded.
+//   n < 64: half a (output channel n); n >= 64: half b (output channel n - 64, tap dj + 4)
+//   m = 0            : channels e,      dj = 2*chunk      + 4*half          (X, even plane)
+//   m = n_mma - 1    : channels e,      dj = 1 + 2*chunk  + 4*half          (X, odd plane)
+//   m = 1 (n_mma = 3): channels 8+(e&3), dj = chunk + 2*(e>>2) + 4*half     (Y', chunk = plane)
+// taps dj > 6 and channels >= C are zero.
+__global__ void pack_stem_fused_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, const float* __restrict__ mean,
+                                       const float* __restrict__ var, float eps, int C, int n_mma,
+                                       __half* __restrict__ wp, float* __restrict__ bias) {
+  const int total = 7 * n_mma * 2 * 128 * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int e = i & 7, n = (i >> 3) & 127, chunk = (i >> 10) & 1;
+    const int m = (i >> 11) % n_mma, di = (i >> 11) / n_mma;
+    const int half = n >> 6, oc = n & 63;
+    int dj, ch;
+    if (m == 0) {
+      dj = 2 * chunk + 4 * half, ch = e;
+    } else if (m == n_mma - 1) {
+      dj = 1 + 2 * chunk + 4 * half, ch = e;
+    } else {
+      dj = chunk + 2 * (e >> 2) + 4 * half, ch = 8 + (e & 3);
+    }
+    float v = 0.f;
+    if (dj < 7 && ch < C) v = w[(((size_t)oc * C + ch) * 7 + di) * 7 + dj] * (gamma[oc] / sqrtf(var[oc] + eps));
+    wp[i] = __float2half_rn(v);
+  }
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 64) bias[i] = beta[i] - mean[i] * gamma[i] / sqrtf(var[i] + eps);
+}
 
 }  // namespace kws
 
 using namespace kws;
 
 static long long* g_fused_dbg = nullptr;
+
 // development aid (not part of the public header): device buffer [148][8] receiving the issuer's cycle counters
 extern "C" void kws_debug_set_fused_counters(long long* dev_buf) { g_fused_dbg = dev_buf; }
 
+static int fused_n_mma(int C) { return C <= 8 ? 2 : 3; }
+
+extern "C" size_t kws_stem_fused_weight_bytes(int C) {
+  return C > 0 && C <= G_MAX_C ? (size_t)7 * fused_n_mma(C) * G_MMA_W_BYTES : 0;
+}
+
+extern "C" int kws_pack_stem_fused(const float* conv_w, const float* gamma, const float* beta, const float* mean,
+                                   const float* var, float eps, int C, void* w_fused, float* bias, void* stream) {
+  KWS_CHECK_ARG(conv_w && gamma && beta && mean && var && w_fused && bias, "pack_stem_fused: null pointer");
+  KWS_CHECK_ARG(C > 0 && C <= G_MAX_C, "pack_stem_fused: C=%d out of (0,%d]", C, G_MAX_C);
+  pack_stem_fused_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(conv_w, gamma, beta, mean, var, eps, C, fused_n_mma(C),
+                                                               (__half*)w_fused, bias);
+  KWS_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int kws_sim_stem_supported(int C, int Tk, int Tu, int Dk) {
-  return C > 0 && C <= F_MAX_C && Dk >= 64 && Dk % 64 == 0 && Tk > 0 && Tu > 0;
+  return C > 0 && C <= G_MAX_C && Dk >= 64 && Dk % 64 == 0 && Tk > 0 && Tu > 0;
 }
 
 extern "C" int kws_sim_stem(const void* kwd_n, const void* utt_n, int C, int K, int U, int Tk, int Tu, int Dk,
-                            int pair_mode, const void* w_packed, const float* bias, int out_mode, void* out,
+                            int pair_mode, const void* w_fused, const float* bias, int out_mode, void* out,
                             void* stream) {
-  return kws_sim_stem_range(kwd_n, utt_n, C, K, U, Tk, Tu, Dk, pair_mode, 0, K, 0, U, w_packed, bias, out_mode, out,
+  return kws_sim_stem_range(kwd_n, utt_n, C, K, U, Tk, Tu, Dk, pair_mode, 0, K, 0, U, w_fused, bias, out_mode, out,
                             stream);
 }
 
 extern "C" int kws_sim_stem_range(const void* kwd_n, const void* utt_n, int C, int K, int U, int Tk, int Tu, int Dk,
-                                  int pair_mode, int k0, int nk, int u0, int nu, const void* w_packed,
+                                  int pair_mode, int k0, int nk, int u0, int nu, const void* w_fused,
                                   const float* bias, int out_mode, void* out, void* stream) {
-  KWS_CHECK_ARG(kwd_n && utt_n && w_packed && bias && out, "sim_stem: null pointer");
+  KWS_CHECK_ARG(kwd_n && utt_n && w_fused && bias && out, "sim_stem: null pointer");
   KWS_CHECK_ARG(C > 0 && K > 0 && U > 0 && Tk > 0 && Tu > 0, "sim_stem: non-positive dimension");
   KWS_CHECK_ARG(k0 >= 0 && nk > 0 && k0 + nk <= K, "sim_stem: keyword range [%d,%d) outside [0,%d)", k0, k0 + nk, K);
   KWS_CHECK_ARG(u0 >= 0 && nu > 0 && u0 + nu <= U, "sim_stem: utterance range [%d,%d) outside [0,%d)", u0, u0 + nu, U);
-  KWS_CHECK_ARG(C <= F_MAX_C, "sim_stem: C=%d > %d layers (use kws_sim + kws_stem)", C, F_MAX_C);
+  KWS_CHECK_ARG(C <= G_MAX_C, "sim_stem: C=%d > %d layers (use kws_sim + kws_stem)", C, G_MAX_C);
   KWS_CHECK_ARG(Dk % 64 == 0 && Dk >= 64, "sim_stem: Dk=%d must be a multiple of 64", Dk);
   KWS_CHECK_ARG(pair_mode == KWS_PAIRS_ALL || pair_mode == KWS_PAIRS_DIAG, "sim_stem: bad pair_mode %d", pair_mode);
   KWS_CHECK_ARG(pair_mode == KWS_PAIRS_ALL || (U == K && k0 == u0 && nk == nu),
                 "sim_stem: KWS_PAIRS_DIAG needs U == K and equal ranges (got K=%d U=%d)", K, U);
   KWS_CHECK_ARG(out_mode == KWS_STEM_OUT_NCHW_F32 || out_mode == KWS_STEM_OUT_NHWC_BF16, "sim_stem: bad out_mode %d",
                 out_mode);
-  KWS_CHECK_ARG((reinterpret_cast<uintptr_t>(w_packed) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+  KWS_CHECK_ARG((reinterpret_cast<uintptr_t>(w_fused) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                 "sim_stem: pointers must be 16-byte aligned");
   CUtensorMap mu, mk;
   {
@@ -454,27 +724,46 @@ extern "C" int kws_sim_stem_range(const void* kwd_n, const void* utt_n, int C, i
                                 CU_TENSOR_MAP_SWIZZLE_128B))
       return e;
   }
+  const int Ho = (Tk + 1) / 2, Wo = (Tu + 1) / 2;
+  const long long n_pairs = (long long)nk * (pair_mode == KWS_PAIRS_DIAG ? 1 : nu);
+  KWS_CHECK_ARG(n_pairs < (1ll << 31), "sim_stem: too many pairs in one launch");
+  CUtensorMap mo_lo, mo_hi;
+  {
+    // bf16 channels-last activation [pairs, Ho, Wo, 64]; one box = 32 (lo warp) or 28 (hi warp: slots 32..59)
+    // pixels x 64 channels of one output row.  (Encoded for the fp32 NCHW mode as well, where it is not used.)
+    const uint64_t dims[4] = {64, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)n_pairs};
+    const uint64_t strides[3] = {128, 128ull * Wo, 128ull * Wo * Ho};
+    const uint32_t box_lo[4] = {64, 32, 1, 1}, box_hi[4] = {64, G_TILE_OJ - 32, 1, 1};
+    if (int e = make_tensor_map(&mo_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, dims, strides, box_lo,
+                                CU_TENSOR_MAP_SWIZZLE_128B))
+      return e;
+    if (int e = make_tensor_map(&mo_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, dims, strides, box_hi,
+                                CU_TENSOR_MAP_SWIZZLE_128B))
+      return e;
+  }
   FusedParams p{};
-  p.w = reinterpret_cast<const uint4*>(w_packed);
+  p.w = reinterpret_cast<const uint4*>(w_fused);
   p.bias = bias;
   p.out = out;
   p.out_mode = out_mode;
   p.C = C, p.K = K, p.U = U, p.Tk = Tk, p.Tu = Tu, p.nkb = Dk / 64;
   p.k0 = k0, p.u0 = u0, p.nk = nk, p.nu = nu;
+  p.n_mma = fused_n_mma(C);
   p.Ho = (Tk + 1) / 2;
   p.Wo = (Tu + 1) / 2;
-  p.col_tiles = (p.Wo + F_TILE_OJ - 1) / F_TILE_OJ;
+  p.col_tiles = (p.Wo + G_TILE_OJ - 1) / G_TILE_OJ;
   p.nP = (p.Ho + 1) / 2;
   p.nQ = p.nP + 2;
   p.n_chunks = (p.nQ + 3) / 4;
   p.diag = pair_mode == KWS_PAIRS_DIAG;
   p.num_items = (long long)nk * (p.diag ? 1 : nu) * p.col_tiles;
-  KWS_CUDA(cudaFuncSetAttribute(kws_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
+  auto kern = out_mode == KWS_STEM_OUT_NHWC_BF16 ? kws_fused_kernel<true> : kws_fused_kernel<false>;
+  KWS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM));
   long long grid = p.num_items;
   const int sms = sm_count();
   if (grid > sms) grid = sms;
   p.dbg = g_fused_dbg;
-  kws_fused_kernel<<<(int)grid, F_THREADS, F_SMEM, (cudaStream_t)stream>>>(mu, mk, p);
+  kern<<<(int)grid, G_THREADS, G_SMEM, (cudaStream_t)stream>>>(mu, mk, mo_lo, mo_hi, p);
   KWS_CUDA(cudaGetLastError());
   return 0;
 }

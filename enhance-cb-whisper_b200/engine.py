@@ -37,6 +37,7 @@ class PackedWeights:
     bt: Optional[torch.Tensor] = None  # fp32 [C,P]
     stem_w: Optional[torch.Tensor] = None  # fp16 [G,49,2,64,8]
     stem_b: Optional[torch.Tensor] = None  # fp32 [64]
+    stem_wf: Optional[torch.Tensor] = None  # fp16, fused-kernel packing (C <= 12), else None
 
     @property
     def Dk(self) -> int:
@@ -70,6 +71,11 @@ def pack_weights(sd: Mapping[str, torch.Tensor], variant: str, C: int, D: int, P
             dev(STEM_KEY + "convolution.weight"), dev(STEM_KEY + "normalization.weight"),
             dev(STEM_KEY + "normalization.bias"), dev(STEM_KEY + "normalization.running_mean"),
             dev(STEM_KEY + "normalization.running_var"))
+        if ops._lib.load().kws_stem_fused_weight_bytes(C):
+            pw.stem_wf, _ = ops.pack_stem_fused(
+                dev(STEM_KEY + "convolution.weight"), dev(STEM_KEY + "normalization.weight"),
+                dev(STEM_KEY + "normalization.bias"), dev(STEM_KEY + "normalization.running_mean"),
+                dev(STEM_KEY + "normalization.running_var"))
     return pw
 
 
@@ -136,7 +142,7 @@ class KWSEngine:
 
     def fused(self, Tk: int, Tu: int) -> bool:
         """True when the single-kernel similarity+stem path covers this model (kws_sim_stem_supported)."""
-        return self.w.stem_w is not None and ops.sim_stem_supported(self.w.C, Tk, Tu, self.w.Dk)
+        return self.w.stem_wf is not None and ops.sim_stem_supported(self.w.C, Tk, Tu, self.w.Dk)
 
     def hot_path(self, kwd_n: torch.Tensor, utt_n: torch.Tensor, out_mode: int, max_pairs: int = 1024,
                  consume: Optional[Callable] = None, bufs: Optional[dict] = None,
@@ -165,7 +171,7 @@ class KWSEngine:
                 ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 ev[0].record()
             if fused:
-                st = ops.sim_stem(kwd_n, utt_n, self.w.stem_w, self.w.stem_b, out_mode, out=bufs[keyo],
+                st = ops.sim_stem(kwd_n, utt_n, self.w.stem_wf, self.w.stem_b, out_mode, out=bufs[keyo],
                                   k_range=(k0, k1), u_range=(u0, u1))
             else:
                 kk = kwd_n[:, k0:k1].contiguous() if (k0, k1) != (0, K) else kwd_n

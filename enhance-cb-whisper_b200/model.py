@@ -182,7 +182,7 @@ class B200ForwardMixin:
             if not self.b200_return_features and eng.fused(Tk_s, Tu_s):
                 # KWSOutput.features is read by no caller of the reference; without it the
                 # similarity tensor never reaches HBM
-                st = ops.sim_stem(kwd_n, utt_n, eng.w.stem_w, eng.w.stem_b, out_mode, diag=diag)
+                st = ops.sim_stem(kwd_n, utt_n, eng.w.stem_wf, eng.w.stem_b, out_mode, diag=diag)
             else:
                 f32, f16 = ops.sim(kwd_n, utt_n, want_f32=self.b200_return_features, want_f16=True, diag=diag)
                 st = ops.stem(f16, Tu_s, eng.w.stem_w, eng.w.stem_b, out_mode)

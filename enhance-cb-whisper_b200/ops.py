@@ -73,6 +73,24 @@ def pack_stem_weights(conv_w, gamma, beta, mean, var, eps: float = BN_EPS) -> Tu
     return wp, bias
 
 
+def pack_stem_fused(conv_w, gamma, beta, mean, var, eps: float = BN_EPS) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Stem conv + BN folded and packed for the fused similarity+stem kernel
+    -> (w_fused fp16 [kws_stem_fused_weight_bytes(C) / 2], bias fp32 [64]); C <= 12."""
+    lib = _lib.load()
+    Cc = conv_w.shape[1]
+    if tuple(conv_w.shape) != (64, Cc, 7, 7):
+        raise KWSError(f"stem conv weight must be [64,C,7,7], got {tuple(conv_w.shape)}")
+    nbytes = lib.kws_stem_fused_weight_bytes(Cc)
+    if nbytes == 0:
+        raise KWSError(f"the fused similarity+stem kernel does not cover C={Cc}")
+    args = [t.detach().float().contiguous() for t in (conv_w, gamma, beta, mean, var)]
+    wf = torch.empty(nbytes // 2, dtype=torch.float16, device=conv_w.device)
+    bias = torch.empty(64, dtype=torch.float32, device=conv_w.device)
+    check(lib.kws_pack_stem_fused(*[_cuda(a, "stem weight", torch.float32) for a in args], eps, Cc,
+                                  _cuda(wf, "w_fused"), _cuda(bias, "bias"), _stream()), "kws_pack_stem_fused")
+    return wf, bias
+
+
 def fold_temporal_weights(conv_w, conv_b, gamma, beta, mean, var, eps: float = BN_EPS):
     """conv_w [C,P,P,3] ... -> (w_folded fp32 [C,3,P,P], b_folded fp32 [C,P])"""
     lib = _lib.load()
@@ -223,10 +241,10 @@ def sim_stem_supported(Cc: int, Tk: int, Tu: int, Dk: int) -> bool:
     return bool(_lib.load().kws_sim_stem_supported(Cc, Tk, Tu, Dk))
 
 
-def sim_stem(kwd_n: torch.Tensor, utt_n: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, out_mode: int,
+def sim_stem(kwd_n: torch.Tensor, utt_n: torch.Tensor, w_fused: torch.Tensor, bias: torch.Tensor, out_mode: int,
              diag: bool = False, out: Optional[torch.Tensor] = None, k_range: Optional[Tuple[int, int]] = None,
              u_range: Optional[Tuple[int, int]] = None) -> torch.Tensor:
-    """Fused similarity + stem.  kwd_n fp16 [C,K,Tk,Dk], utt_n fp16 [C,U,Tu,Dk] -> stem activation of the
+    """Fused similarity + stem (w_fused from pack_stem_fused).  kwd_n fp16 [C,K,Tk,Dk], utt_n fp16 [C,U,Tu,Dk] -> stem activation of the
     pairs of keywords k_range=(k0,k1) x utterances u_range=(u0,u1) (default: all), pair = (k-k0)*(u1-u0) + (u-u0)
     (DIAG: pair = k-k0): NCHW fp32 [N,64,Ho,Wo] or channels_last bf16.  ``out`` may be a larger reused
     buffer (its first N pairs are written)."""
@@ -249,7 +267,7 @@ def sim_stem(kwd_n: torch.Tensor, utt_n: torch.Tensor, w_packed: torch.Tensor, b
             raise KWSError(f"out buffer too small / wrong dtype for {pairs} pairs")
     check(lib.kws_sim_stem_range(_cuda(kwd_n, "kwd_n", torch.float16), _cuda(utt_n, "utt_n", torch.float16), Cc, K,
                                  U, Tk, Tu, Dk, PAIRS_DIAG if diag else PAIRS_ALL, k0, k1 - k0, u0, u1 - u0,
-                                 _cuda(w_packed, "w_packed", torch.float16), _cuda(bias, "bias", torch.float32),
+                                 _cuda(w_fused, "w_fused", torch.float16), _cuda(bias, "bias", torch.float32),
                                  out_mode, _cuda(out, "out"), _stream()), "kws_sim_stem")
     shape = (pairs, 64, Ho, Wo) if f32 else (pairs, Ho, Wo, 64)
     view = out.view(-1)[: pairs * 64 * Ho * Wo].view(shape)

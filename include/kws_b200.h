@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define KWS_ABI_VERSION 2
+#define KWS_ABI_VERSION 3
 
 /* 16-bit operand formats (same encoding as the tcgen05 kind::f16 descriptor) */
 #define KWS_F16 0  /* IEEE half: 10-bit mantissa; for L2-normalised data and sane weights */
@@ -70,6 +70,14 @@ int kws_sm_count(void);
 int kws_pack_stem_weights(const float* conv_w, const float* gamma, const float* beta, const float* mean,
                           const float* var, float eps, int C, void* w_packed, float* bias, void* stream);
 size_t kws_stem_weight_bytes(int C);
+
+/* The same fold, packed for the fused similarity+stem kernel (kws_sim_stem*): per kernel row the seven
+ * taps x C channels are laid out as 2 (C <= 8) or 3 (C <= 12) N=128 B-operands, two taps per MMA and
+ * channels 8..11 of two neighbouring pixels per 16-byte chunk (layout documented in csrc/kws_fused.cu).
+ *   w_fused fp16, kws_stem_fused_weight_bytes(C) bytes (0 if the fused kernel does not cover C)        */
+int kws_pack_stem_fused(const float* conv_w, const float* gamma, const float* beta, const float* mean,
+                        const float* var, float eps, int C, void* w_fused, float* bias, void* stream);
+size_t kws_stem_fused_weight_bytes(int C);
 
 /* Fold BatchNorm1d (eval) into the LEF temporal Conv1d.
  * time_projector[i] = Conv1d(P,P,3,pad 1) -> BatchNorm1d -> MaxPool1d(3,2,1)
@@ -147,11 +155,11 @@ size_t kws_stem_workspace_bytes(int pairs, int C, int Tk, int Tu);
  * reaching HBM -- similarity tiles go TMEM -> fp16 shared-memory ring -> stem MMAs in one kernel
  * (replaces model.py:174-191,:217 and HF modeling_resnet.py:39-54 via resnet.py:38,53 together).
  *   kwd_n fp16 [C,K,Tk,Dk], utt_n fp16 [C,U,Tu,Dk] (prepared operands, mask folded)
- *   w_packed/bias from kws_pack_stem_weights; pair_mode / out_mode / out as kws_sim / kws_stem
+ *   w_fused/bias from kws_pack_stem_fused; pair_mode / out_mode / out as kws_sim / kws_stem
  *   Requires C <= 12 and Dk % 64 == 0 (kws_sim_stem_supported() != 0); other shapes use
  *   kws_sim + kws_stem.                                                                     */
 int kws_sim_stem(const void* kwd_n, const void* utt_n, int C, int K, int U, int Tk, int Tu, int Dk, int pair_mode,
-                 const void* w_packed, const float* bias, int out_mode, void* out, void* stream);
+                 const void* w_fused, const float* bias, int out_mode, void* out, void* stream);
 int kws_sim_stem_supported(int C, int Tk, int Tu, int Dk);
 /* Same kernel over a sub-block of the pair grid: keywords [k0, k0+nk) x utterances [u0, u0+nu) of the
  * resident operand banks (K, U stay the bank sizes).  out holds nk*nu pairs, pair = (k-k0)*nu + (u-u0)
@@ -159,7 +167,7 @@ int kws_sim_stem_supported(int C, int Tk, int Tu, int Dk);
  * test_step group loop (model.py:769-780) streams a K x U job through a bounded activation buffer
  * without re-packing operand slabs. */
 int kws_sim_stem_range(const void* kwd_n, const void* utt_n, int C, int K, int U, int Tk, int Tu, int Dk,
-                       int pair_mode, int k0, int nk, int u0, int nu, const void* w_packed, const float* bias,
+                       int pair_mode, int k0, int nk, int u0, int nu, const void* w_fused, const float* bias,
                        int out_mode, void* out, void* stream);
 
 /* ---- scores ---------------------------------------------------------------- */

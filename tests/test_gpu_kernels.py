@@ -166,6 +166,12 @@ def pack_stem(ops, sd):
                                  sd[O.STEM + "normalization.running_var"])
 
 
+def pack_stem_fused(ops, sd):
+    return ops.pack_stem_fused(sd[O.STEM + "convolution.weight"], sd[O.STEM + "normalization.weight"],
+                               sd[O.STEM + "normalization.bias"], sd[O.STEM + "normalization.running_mean"],
+                               sd[O.STEM + "normalization.running_var"])
+
+
 @pytest.mark.parametrize("N,Cc,Tk,Tu", [(1, 3, 8, 40), (2, 3, 22, 70), (2, 12, 23, 301), (1, 16, 150, 1500),
                                         (1, 4, 1, 1), (1, 32, 21, 135), (2, 20, 9, 260)])
 def test_stem_matches_conv(ops, cuda_dev, N, Cc, Tk, Tu):
@@ -195,16 +201,18 @@ def test_sim_stem_fused_matches_unfused_and_conv(ops, cuda_dev, Cc, K, U, Tk, Tu
     un[:, -1, (2 * Tu) // 3:] = 0
     sd = {k: v.to(cuda_dev) for k, v in O.make_weights("L", Cc, 64, seed=9).items()}
     wp, bias = pack_stem(ops, sd)
+    wf, bias_f = pack_stem_fused(ops, sd)
+    assert torch.equal(bias, bias_f)
     assert ops.sim_stem_supported(Cc, Tk, Tu, Dk)
     _, f16 = ops.sim(kn, un, False, True)
     exp = stem_expect(f16, Tu, sd)
     ref = ops.stem(f16, Tu, wp, bias, ops.STEM_OUT_NCHW_F32)
-    out = ops.sim_stem(kn, un, wp, bias, ops.STEM_OUT_NCHW_F32)
+    out = ops.sim_stem(kn, un, wf, bias, ops.STEM_OUT_NCHW_F32)
     assert out.shape == exp.shape == ref.shape
     tol = 3e-4 * max(1.0, exp.abs().max().item())
     assert maxerr(out, exp) <= tol
     assert maxerr(out, ref) <= tol
-    o2 = ops.sim_stem(kn, un, wp, bias, ops.STEM_OUT_NHWC_BF16)
+    o2 = ops.sim_stem(kn, un, wf, bias, ops.STEM_OUT_NHWC_BF16)
     assert maxerr(o2, exp) <= 2e-2 * max(1.0, exp.abs().max().item() / 4)
 
 
@@ -216,14 +224,15 @@ def test_sim_stem_fused_diag_and_many_items(ops, cuda_dev):
     un = unit_rows(Cc, U, Tu, Dk, g=g, dev=cuda_dev).half()
     sd = {k: v.to(cuda_dev) for k, v in O.make_weights("L", Cc, 64, seed=3).items()}
     wp, bias = pack_stem(ops, sd)
+    wf, _ = pack_stem_fused(ops, sd)
     _, f16 = ops.sim(kn, un, False, True)
     ref = ops.stem(f16, Tu, wp, bias, ops.STEM_OUT_NCHW_F32)
-    out = ops.sim_stem(kn, un, wp, bias, ops.STEM_OUT_NCHW_F32)
+    out = ops.sim_stem(kn, un, wf, bias, ops.STEM_OUT_NCHW_F32)
     assert maxerr(out, ref) <= 3e-4 * max(1.0, ref.abs().max().item())
     un2 = unit_rows(Cc, K, Tu, Dk, g=g, dev=cuda_dev).half()
     _, f16d = ops.sim(kn, un2, False, True, diag=True)
     refd = ops.stem(f16d, Tu, wp, bias, ops.STEM_OUT_NCHW_F32)
-    outd = ops.sim_stem(kn, un2, wp, bias, ops.STEM_OUT_NCHW_F32, diag=True)
+    outd = ops.sim_stem(kn, un2, wf, bias, ops.STEM_OUT_NCHW_F32, diag=True)
     assert outd.shape == refd.shape
     assert maxerr(outd, refd) <= 3e-4 * max(1.0, refd.abs().max().item())
 
@@ -236,7 +245,7 @@ def test_sim_stem_range_is_a_block_of_the_full_job(ops, cuda_dev):
     kn = unit_rows(Cc, K, Tk, Dk, g=g, dev=cuda_dev).half()
     un = unit_rows(Cc, U, Tu, Dk, g=g, dev=cuda_dev).half()
     sd = {k: v.to(cuda_dev) for k, v in O.make_weights("L", Cc, 64, seed=5).items()}
-    wp, bias = pack_stem(ops, sd)
+    wp, bias = pack_stem_fused(ops, sd)
     full = ops.sim_stem(kn, un, wp, bias, ops.STEM_OUT_NCHW_F32)  # [K*U,64,Ho,Wo]
     full = full.view(K, U, *full.shape[1:])
     buf = torch.full((K * U * full[0, 0].numel(),), float("nan"), device=cuda_dev)

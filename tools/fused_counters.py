@@ -9,11 +9,14 @@ g = torch.Generator(device=dev).manual_seed(7)
 Cc, K, U, Tk, Tu, P = 12, 74, 2, 150, 1500, 64
 unit = lambda *s: torch.nn.functional.normalize(torch.randn(*s, generator=g, device=dev), dim=-1)
 kn, un = unit(Cc, K, Tk, P).half(), unit(Cc, U, Tu, P).half()
-wp, bias = ops.pack_stem_weights(torch.randn(64, Cc, 7, 7, generator=g, device=dev) * 0.05, torch.ones(64, device=dev),
+wp, bias = ops.pack_stem_fused(torch.randn(64, Cc, 7, 7, generator=g, device=dev) * 0.05, torch.ones(64, device=dev),
                                  torch.zeros(64, device=dev), torch.zeros(64, device=dev), torch.ones(64, device=dev))
 out = torch.empty(K * U, 75, 750, 64, dtype=torch.bfloat16, device=dev)
 ops.sim_stem(kn, un, wp, bias, ops.STEM_OUT_NHWC_BF16, out=out)
-buf = torch.zeros(148, 8, dtype=torch.int64, device=dev)
+if len(sys.argv) > 1:
+    _lib.load().kws_debug_set_fused_skip(int(sys.argv[1]))
+    print("dbg_skip", sys.argv[1])
+buf = torch.zeros(148, 32, dtype=torch.int64, device=dev)
 lib = _lib.load()
 lib.kws_debug_set_fused_counters.argtypes = [ctypes.c_void_p]
 lib.kws_debug_set_fused_counters(buf.data_ptr())
@@ -24,3 +27,7 @@ b = buf.double().mean(0).tolist()
 items = K * U * 13 / 148
 print(f"per item (mean over CTAs, {items:.1f} items/CTA): total {b[0]/items:.0f} cyc | deadline-sim wait {b[1]/items:.0f} | "
       f"aempty wait {b[2]/items:.0f} | qfull wait {b[3]/items:.0f} | issue {b[4]/items:.0f}")
+print(f"  epilogue: afull wait {b[5]/items:.0f} | until acc released {b[6]/items:.0f} | whole step body {b[7]/items:.0f}")
+print(f"  converter: sfull wait {b[8]/items:.0f} | tmem ld {b[9]/items:.0f} | qempty wait {b[10]/items:.0f} | pack+store {b[11]/items:.0f}")
+print("  epilogue phases per item: " + " | ".join(f"{n} {b[16+i]/items:.0f}" for i, n in enumerate(
+    ["g0 ld+wait", "g0 mbox+bar", "g0 shfl+math+sts", "g1 ld+wait", "g1 mbox+bar", "g1 shfl+math+sts", "fence+tma"])))

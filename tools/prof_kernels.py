@@ -83,7 +83,7 @@ def main():
     if want("fused"):
         conv_w = torch.randn(64, Cc, 7, 7, generator=g, device=dev) * 0.05
         one, zero = torch.ones(64, device=dev), torch.zeros(64, device=dev)
-        wp, bias = ops.pack_stem_weights(conv_w, one, zero, zero, one)
+        wp, bias = ops.pack_stem_fused(conv_w, one, zero, zero, one)
         out = torch.empty(pairs, 75, 750, 64, dtype=torch.bfloat16, device=dev)
         t = timeit(lambda: ops.sim_stem(kn, un, wp, bias, ops.STEM_OUT_NHWC_BF16, out=out), a.iters)
         fl = (2.0 * 64 * 49 * Cc * 75 * 750 + 2.0 * Cc * Tk * Tu * P) * pairs
