@@ -44,6 +44,10 @@ def _stale(target: str, deps) -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ_DIR, exist_ok=True)
+    flags = list(NVCC_FLAGS)
+    if os.environ.get("KWS_FUSED_TIMERS"):  # development aid: per-role cycle counters in the fused kernel
+        flags.append("-DKWS_FUSED_TIMERS")
+        force = True
     headers = [os.path.join(CSRC, "kws_common.cuh"), os.path.join(INCLUDE, "kws_b200.h"), os.path.abspath(__file__)]
     nvcc = _nvcc()
 
@@ -51,7 +55,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         s = os.path.join(CSRC, src)
         o = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-c", s, "-o", o]
+            cmd = [nvcc] + flags + ["-I", INCLUDE, "-c", s, "-o", o]
             r = subprocess.run(cmd, capture_output=True, text=True)
             if r.returncode != 0:
                 raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")

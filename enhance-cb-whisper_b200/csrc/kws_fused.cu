@@ -41,17 +41,27 @@
 // store into the ring, one quantum (4 rows) per stem step.
 //
 // TMEM: stem accumulators [0,128) and [128,256) (double-buffered), similarity region [256, 256+16C).
-// Roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer (one elected thread; similarity stages
-// are slipped between the stem's kernel rows), warp 2 TMEM allocator, warps 4..7 stem epilogue,
-// warps 8..11 converters.
+// Roles (384 threads): warp 0 TMA producer, warp 1 stem MMA issuer, warp 2 TMEM allocator + similarity MMA
+// issuer (one elected thread each: two independent instruction streams into the one tensor pipe, so the
+// barrier polls of one never starve it), warps 4..7 stem epilogue, warps 8..11 converters.
 #include "kws_common.cuh"
 #include "../../include/kws_b200.h"
 
 // cycle counters of the roles (development aid): compiled in only with -DKWS_FUSED_TIMERS, they cost registers
 #ifdef KWS_FUSED_TIMERS
 #define KWS_CLK() clock64()
+// event trace of CTA 0: dbg[148*32 + (role*KWS_TRACE_STEPS + step)*8 + k] = clock64()
+#define KWS_TRACE_STEPS 640
+#define KWS_TRACE(role, step, k)                                                                   \
+  do {                                                                                             \
+    if (p.dbg && blockIdx.x == 0 && (step) < KWS_TRACE_STEPS)                                      \
+      p.dbg[148 * 32 + ((role)*KWS_TRACE_STEPS + (step)) * 8 + (k)] = clock64();                   \
+  } while (0)
 #else
 #define KWS_CLK() 0ll
+#define KWS_TRACE(role, step, k) \
+  do {                           \
+  } while (0)
 #endif
 
 namespace kws {
@@ -73,7 +83,8 @@ constexpr int G_MAX_C = 12;
 constexpr int G_ACC_COLS = 128;                    // one stem accumulator: half a | half b
 constexpr int G_TMEM_SIM = 2 * G_ACC_COLS;         // similarity region starts at column 256
 constexpr int G_OUT_STAGE = 4 * 32 * 128;          // per epilogue warp: 32 pixels x 64 bf16 (SW128), source of its TMA stores
-constexpr int G_NBAR = 2 * G_NS + 1 + 1 + 4 + 4 + 2 + 2;
+constexpr int G_NPAIR = G_MAX_C / 2;                 // similarity tiles are handed over per pair of layers
+constexpr int G_NBAR = 2 * G_NS + 2 * G_NPAIR + 4 + 4 + 2 + 2;
 
 struct FusedParams {
   const uint4* w;     // fused stem weights (kws_pack_stem_fused)
@@ -159,9 +170,9 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + G_RING_BYTES);
   uint64_t* ofull = bars;                 // [G_NS] TMA -> MMA (similarity operands)
   uint64_t* oempty = ofull + G_NS;        // [G_NS] MMA commit -> TMA
-  uint64_t* sfull = oempty + G_NS;        // [1] MMA commit -> converters (similarity region ready)
-  uint64_t* sempty = sfull + 1;           // [1] converters -> MMA
-  uint64_t* qfull = sempty + 1;           // [4] converters -> MMA (ring quantum written)
+  uint64_t* sfull = oempty + G_NS;        // [G_NPAIR] MMA commit -> converters (similarity tiles of a layer pair ready)
+  uint64_t* sempty = sfull + G_NPAIR;     // [G_NPAIR] converters -> MMA (tiles pulled into registers)
+  uint64_t* qfull = sempty + G_NPAIR;     // [4] converters -> MMA (ring quantum written)
   uint64_t* qempty = qfull + 4;           // [4] MMA commit -> converters
   uint64_t* afull = qempty + 4;           // [2] MMA commit -> epilogue (stem accumulator ready)
   uint64_t* aempty = afull + 2;           // [2] epilogue -> MMA
@@ -197,8 +208,10 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
       mbar_init(&ofull[s], 1);
       mbar_init(&oempty[s], 1);
     }
-    mbar_init(&sfull[0], 1);
-    mbar_init(&sempty[0], 128);
+    for (int s = 0; s < G_NPAIR; ++s) {
+      mbar_init(&sfull[s], 1);
+      mbar_init(&sempty[s], 128);
+    }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&afull[s], 1);
       mbar_init(&aempty[s], 128);
@@ -245,81 +258,70 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (one elected thread) =====================
+  } else if (warp == 2) {
+    // ===================== similarity MMA issuer (one elected thread) =====================
+    // Runs as far ahead as the operand stages and the single TMEM region allow; its barrier polls never
+    // hold up the stem issuer (warp 1), and its MMAs fill the tensor pipe while that one polls.
     if (elect_one()) {
       const uint32_t idesc_sim = make_idesc_f16(128, 16, 0);
-      const uint32_t idesc_stem = make_idesc_f16(128, 2 * G_OC, 0);
       const uint32_t ops_u32 = smem_u32(s_ops);
+      const uint64_t sdesc0 = make_smem_desc(0, 16, 1024, LAYOUT_SW128);
+      int o_stage = 0;
+      uint32_t o_phase = 0, g = 0;
+      for (long long it = blockIdx.x; it < p.num_items; it += gridDim.x) {
+        for (int n = 0; n < p.n_chunks; ++n, ++g) {
+          for (int st = 0; st < stages_per_chunk; ++st) {
+            const int c = st / p.nkb, kb = st - c * p.nkb;
+            // the converters have pulled the previous chunk's tiles of this layer pair out of TMEM
+            if (kb == 0 && (c & 1) == 0) mbar_wait(&sempty[c >> 1], (g & 1) ^ 1, 500 + (c >> 1));
+            mbar_wait(&ofull[o_stage], o_phase, 300 + o_stage);
+            tc_fence_after();
+            const uint32_t d = G_TMEM_SIM + c * 16;  // TMEM base is 0 (checked at start)
+            const uint32_t sa = ops_u32 + o_stage * G_STAGE;
+            const uint64_t adesc = sdesc0 + (uint64_t)(sa >> 4);
+            const uint64_t bdesc = adesc + (uint64_t)(G_A_BYTES >> 4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16(d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc_sim, (kb | k) != 0);
+            umma_commit(&oempty[o_stage]);
+            if (++o_stage == G_NS) o_stage = 0, o_phase ^= 1;
+            // layer pair complete (or last layer of an odd C): hand its tiles to the converters
+            if (kb == p.nkb - 1 && ((c & 1) == 1 || c == p.C - 1)) umma_commit(&sfull[c >> 1]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== stem MMA issuer (one elected thread) =====================
+    if (elect_one()) {
+      const uint32_t idesc_stem = make_idesc_f16(128, 2 * G_OC, 0);
       // A descriptors: SBO = 128 (8 pixels x 16 B); LBO = distance between the two 8-element K chunks
       const uint64_t adesc_px = make_smem_desc(smem_u32(s_ring), 16, 128, LAYOUT_NONE);        // +1 pixel
       const uint64_t adesc_pl = make_smem_desc(smem_u32(s_ring), G_BLOCK, 128, LAYOUT_NONE);   // other plane
       const uint64_t bdesc0 = make_smem_desc(smem_u32(s_w), 128 * 16, 128, LAYOUT_NONE);
-      const uint64_t sdesc0 = make_smem_desc(0, 16, 1024, LAYOUT_SW128);
       const int n_mma = p.n_mma;
-      // similarity cursor: runs ahead of the stem cursor (across items)
-      long long s_it = blockIdx.x;
-      int s_chunk = 0, s_stage = 0;
-      uint32_t s_g = 0;  // similarity chunks fully issued so far (global)
-      int o_stage = 0;
-      uint32_t o_phase = 0;
-      // one operand stage = 4 MMAs of one layer / k-block; non-blocking calls return false when the
-      // TMEM region or the operands are not there yet (the stem MMAs go on, the call is retried)
-      auto sim_issue = [&](bool blocking) -> bool {
-        if (s_stage == 0 && !mbar_poll(&sempty[0], (s_g & 1) ^ 1, blocking, 500)) return false;
-        if (!mbar_poll(&ofull[o_stage], o_phase, blocking, 300 + o_stage)) return false;
-        tc_fence_after();
-        const int c = s_stage / p.nkb, kb = s_stage - c * p.nkb;
-        const uint32_t d = G_TMEM_SIM + c * 16;  // TMEM base is 0 (checked at start)
-        const uint32_t sa = ops_u32 + o_stage * G_STAGE;
-        const uint64_t adesc = sdesc0 + (uint64_t)(sa >> 4);
-        const uint64_t bdesc = adesc + (uint64_t)(G_A_BYTES >> 4);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16(d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc_sim, (kb | k) != 0);
-        umma_commit(&oempty[o_stage]);
-        if (++o_stage == G_NS) o_stage = 0, o_phase ^= 1;
-        if (++s_stage == stages_per_chunk) {
-          umma_commit(&sfull[0]);
-          s_stage = 0;
-          ++s_g;
-          if (++s_chunk == p.n_chunks) s_chunk = 0, s_it += gridDim.x;
-        }
-        return true;
-      };
-
-      uint32_t g_chunk0 = 0;  // global index of the current item's chunk 0
-      uint32_t qbase = 0;     // global index of the current item's quantum 0
-      uint32_t acc_seq = 0;   // global stem step counter -> accumulator buffer
-      long long tm_sim = 0, tm_acc = 0, tm_q = 0, tm_issue = 0;
+      uint32_t qbase = 0;    // global index of the current item's quantum 0
+      uint32_t acc_seq = 0;  // global stem step counter -> accumulator buffer
+      long long tm_acc = 0, tm_q = 0, tm_issue = 0;
       const long long tm_start = KWS_CLK();
       for (long long it = blockIdx.x; it < p.num_items; it += gridDim.x) {
         int waited = 0;  // quanta of this item known to be in the ring
         for (int P = 0; P < p.nP; ++P, ++acc_seq) {
-          // chunks: `need` holds quantum P+2 and must be issued now; `ahead` (one chunk further,
-          // possibly chunk 0 of the next item) is issued a stage at a time while the stem runs
-          int need = (P + 2) >> 2;
-          if (need > p.n_chunks - 1) need = p.n_chunks - 1;
-          int ahead = ((P + 2) >> 2) + 1;
-          if (ahead > p.n_chunks) ahead = p.n_chunks;
-          const uint32_t g_need = g_chunk0 + (uint32_t)need, g_ahead = g_chunk0 + (uint32_t)ahead;
           const uint32_t acc = acc_seq & 1;
           const long long t1 = KWS_CLK();
+          KWS_TRACE(0, acc_seq, 0);
           mbar_wait(&aempty[acc], ((acc_seq >> 1) & 1) ^ 1, 200 + acc);
+          KWS_TRACE(0, acc_seq, 1);
           const long long t2 = KWS_CLK();
-          // kernel rows 0..5 read quanta P and P+1 only; quantum P+2 (input row 4P+5) is first touched by di = 6.
-          // A quantum may only be waited for once its similarity chunk has been issued (else: deadlock).
-          {
-            int c1 = (P + 1) >> 2;
-            if (c1 > p.n_chunks - 1) c1 = p.n_chunks - 1;
-            while (s_g <= g_chunk0 + (uint32_t)c1 && s_it < p.num_items) sim_issue(true);
-          }
-          while (waited <= P + 1 && waited < p.nQ) {
+          // kernel rows 0..5 read quanta P and P+1 only; quantum P+2 (input row 4P+5) is first touched by di = 6
+          while (waited <= P + 1 && waited < p.nQ) {  // first step of an item only
             const uint32_t G = qbase + waited;
             mbar_wait(&qfull[G & 3], (G >> 2) & 1, 400 + (int)(G & 3));
             ++waited;
           }
           const long long t3 = KWS_CLK();
+          KWS_TRACE(0, acc_seq, 2);
           tm_acc += t2 - t1, tm_q += t3 - t2;
           tc_fence_after();
           const uint32_t d = acc * G_ACC_COLS;
@@ -327,16 +329,15 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
 #pragma unroll
           for (int di = 0; di < 7; ++di) {
             if (di == 6) {
-              // the chunk holding quantum P+2 must have been issued before we may block on that quantum
               const long long u0 = KWS_CLK();
-              while (s_g <= g_need && s_it < p.num_items) sim_issue(true);
-              const long long u1 = KWS_CLK();
+              KWS_TRACE(0, acc_seq, 3);
               while (waited <= P + 2 && waited < p.nQ) {
                 const uint32_t G = qbase + waited;
                 mbar_wait(&qfull[G & 3], (G >> 2) & 1, 400 + (int)(G & 3));
                 ++waited;
               }
-              tm_sim += u1 - u0, tm_q += KWS_CLK() - u1;
+              tm_q += KWS_CLK() - u0;
+              KWS_TRACE(0, acc_seq, 5);
               tc_fence_after();
             }
             const uint32_t slot0 = (slot_base + (di >> 1)) & (G_NR - 1);
@@ -353,21 +354,20 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
             // (X plane1 | +1 px): half a taps 1,3; half b tap 5
             umma_f16(d, adesc_px + (uint64_t)(row16 + (G_BLOCK >> 4)),
                      b_row + (uint64_t)(((n_mma - 1) * G_MMA_W_BYTES) >> 4), idesc_stem, 1);
-            // similarity stages of the next chunk(s) ride along, two per kernel row
-            if (s_g <= g_ahead && s_it < p.num_items) sim_issue(false);
+            // quantum P (input rows 4P-3..4P) is read by kernel rows 0..3 only: hand its ring slots back early
+            if (di == 3) umma_commit(&qempty[(qbase + P) & 3]);
           }
-          umma_commit(&qempty[(qbase + P) & 3]);  // quantum P is dead once these MMAs retire
           umma_commit(&afull[acc]);
+          KWS_TRACE(0, acc_seq, 6);
           tm_issue += KWS_CLK() - t3;
         }
         // the two tail quanta were read by the last step only
         for (int q = p.nP; q < p.nQ; ++q) umma_commit(&qempty[(qbase + q) & 3]);
         qbase += p.nQ;
-        g_chunk0 += p.n_chunks;
       }
       if (p.dbg) {
         long long* o = p.dbg + (size_t)blockIdx.x * 32;
-        o[0] = KWS_CLK() - tm_start, o[1] = tm_sim, o[2] = tm_acc, o[3] = tm_q, o[4] = tm_issue;
+        o[0] = KWS_CLK() - tm_start, o[1] = 0, o[2] = tm_acc, o[3] = tm_q, o[4] = tm_issue;
       }
     }
     __syncwarp();
@@ -400,6 +400,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
         const long long e0 = KWS_CLK();
         mbar_wait(&afull[acc], (acc_seq >> 1) & 1, 600 + acc);
         const long long e1 = KWS_CLK();
+        if (warp == 4 && lane == 0) KWS_TRACE(1, acc_seq, 0);
         te_wait += e1 - e0;
         tc_fence_after();
         const uint32_t t_row = tmem_base + acc * G_ACC_COLS + ((uint32_t)(q * 32) << 16);
@@ -430,6 +431,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
           if (grp == 1) {  // last TMEM read of this accumulator
             tc_fence_before();
             mbar_arrive(&aempty[acc]);
+            if (warp == 4 && lane == 0) KWS_TRACE(1, acc_seq, 1);
             te_ld += KWS_CLK() - e1;
           }
           float* mbox = grp == 0 ? mbox0 : mbox1;
@@ -516,6 +518,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
           }
         }
         te_rest += KWS_CLK() - e1;
+        if (warp == 4 && lane == 0) KWS_TRACE(1, acc_seq, 2);
         tp[6] += KWS_CLK() - tp[7];
       }
     }
@@ -543,38 +546,36 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
       for (int q0 = 0; q0 < p.nQ; q0 += 4, ++g) {
         const int nq = p.nQ - q0 < 4 ? p.nQ - q0 : 4;
         const long long c0 = KWS_CLK();
-        mbar_wait(&sfull[0], g & 1, 700);
-        tc_fence_after();
-        const long long c1 = KWS_CLK();
-        uint4 px[4][4];  // [quantum][row] channels 0..7
-        uint2 py[4][4];  // [quantum][row] channels 8..11
+        const long long c1 = c0;
+        if (warp == 8 && lane == 0) KWS_TRACE(2, g, 0);
+        // pull the chunk layer pair by layer pair (16 rows x 2 layers per TMEM round trip); each pair's tiles go
+        // back to the similarity issuer at once, so the next chunk is computed while this one is still being pulled
+        uint32_t h2[16][G_NPAIR];  // [row][layer pair] fp16x2
 #pragma unroll
-        for (int qq = 0; qq < 4; ++qq) {
-          if (qq < nq) {
-            uint32_t v[G_MAX_C][4];
+        for (int j = 0; j < G_NPAIR; ++j) {
+          if (2 * j < p.C) {
+            mbar_wait(&sfull[j], g & 1, 700 + j);
+            tc_fence_after();
+            uint32_t v0[16], v1[16];
+            tmem_ld16(t_lane + (2 * j) * 16, v0);
+            if (2 * j + 1 < p.C) {
+              tmem_ld16(t_lane + (2 * j + 1) * 16, v1);
+            } else {
 #pragma unroll
-            for (int c = 0; c < G_MAX_C; ++c) {
-              if (c < p.C) {
-                tmem_ld4(t_lane + c * 16 + qq * 4, v[c]);
-              } else {
-                v[c][0] = v[c][1] = v[c][2] = v[c][3] = 0u;  // +0.0f
-              }
+              for (int r = 0; r < 16; ++r) v1[r] = 0u;
             }
             tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&sempty[j]);
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              px[qq][t] = make_uint4(pack_half2(__uint_as_float(v[0][t]), __uint_as_float(v[1][t])),
-                                     pack_half2(__uint_as_float(v[2][t]), __uint_as_float(v[3][t])),
-                                     pack_half2(__uint_as_float(v[4][t]), __uint_as_float(v[5][t])),
-                                     pack_half2(__uint_as_float(v[6][t]), __uint_as_float(v[7][t])));
-              py[qq][t] = make_uint2(pack_half2(__uint_as_float(v[8][t]), __uint_as_float(v[9][t])),
-                                     pack_half2(__uint_as_float(v[10][t]), __uint_as_float(v[11][t])));
-            }
+            for (int r = 0; r < 16; ++r) h2[r][j] = pack_half2(__uint_as_float(v0[r]), __uint_as_float(v1[r]));
+          } else {
+#pragma unroll
+            for (int r = 0; r < 16; ++r) h2[r][j] = 0u;
           }
         }
-        tc_fence_before();
-        mbar_arrive(&sempty[0]);  // the region may be refilled
         const long long c2 = KWS_CLK();
+        if (warp == 8 && lane == 0) KWS_TRACE(2, g, 1);
         tc_sfull += c1 - c0, tc_ld += c2 - c1;
 #pragma unroll
         for (int qq = 0; qq < 4; ++qq) {
@@ -582,25 +583,29 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
             const long long c3 = KWS_CLK();
             mbar_wait(&qempty[Gq & 3], ((Gq >> 2) & 1) ^ 1, 800 + (int)(Gq & 3));
             const long long c4 = KWS_CLK();
+            if (warp == 8 && lane == 0) KWS_TRACE(3, Gq, 0);
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
               // input row r = 4q + t - 3: parity (t+1)&1, ring slot (2 Gq + (t >> 1)) mod NR
               const uint32_t slot = (2 * Gq + (t >> 1)) & (G_NR - 1);
               uint8_t* d0 = dst_px + ((t + 1) & 1) * 2 * G_BLOCK + slot * 1024;
-              *reinterpret_cast<uint4*>(d0) = px[qq][t];
-              if (slot == 0) *reinterpret_cast<uint4*>(d0 + G_NR * 1024) = px[qq][t];  // mirror: tap windows never wrap
+              const uint4 vx = make_uint4(h2[4 * qq + t][0], h2[4 * qq + t][1], h2[4 * qq + t][2], h2[4 * qq + t][3]);
+              *reinterpret_cast<uint4*>(d0) = vx;
+              if (slot == 0) *reinterpret_cast<uint4*>(d0 + G_NR * 1024) = vx;  // mirror: tap windows never wrap
               if (yp) {
+                const uint2 vy = make_uint2(h2[4 * qq + t][4], h2[4 * qq + t][5]);
                 uint8_t* dy = d0 + 4 * G_BLOCK;
-                *reinterpret_cast<uint2*>(dy) = py[qq][t];                    // own chunk, elements 0..3
-                if (has_left) *reinterpret_cast<uint2*>(dy - 8) = py[qq][t];  // left neighbour's chunk, elements 4..7
+                *reinterpret_cast<uint2*>(dy) = vy;                    // own chunk, elements 0..3
+                if (has_left) *reinterpret_cast<uint2*>(dy - 8) = vy;  // left neighbour's chunk, elements 4..7
                 if (slot == 0) {
-                  *reinterpret_cast<uint2*>(dy + G_NR * 1024) = py[qq][t];
-                  if (has_left) *reinterpret_cast<uint2*>(dy + G_NR * 1024 - 8) = py[qq][t];
+                  *reinterpret_cast<uint2*>(dy + G_NR * 1024) = vy;
+                  if (has_left) *reinterpret_cast<uint2*>(dy + G_NR * 1024 - 8) = vy;
                 }
               }
             }
             fence_proxy_async();
             mbar_arrive(&qfull[Gq & 3]);
+            if (warp == 8 && lane == 0) KWS_TRACE(3, Gq, 1);
             ++Gq;
             tc_qempty += c4 - c3, tc_st += KWS_CLK() - c4;
           }
