@@ -37,13 +37,22 @@
 //
 // The similarity GEMM works on chunks of 16 input rows: for each layer c, D[128 px, 16 rows] =
 // utt tile (128 x Dk, TMA, OOB columns zero-filled = the conv's zero padding) x kwd rows (16 x Dk)^T,
-// fp32 in TMEM; 4 converter warps (thread = pixel) read 4 rows x C layers at a time, pack fp16 and
-// store into the ring, one quantum (4 rows) per stem step.
+// fp32 in TMEM.  4 converter warps (thread = pixel) pull a chunk out of TMEM layer pair by layer pair
+// (each pair's tiles are handed back to the similarity issuer at once, so the next chunk is computed
+// while this one is still being pulled), keep it as packed fp16 in registers and feed the ring one
+// quantum (4 rows) per stem step.
 //
 // TMEM: stem accumulators [0,128) and [128,256) (double-buffered), similarity region [256, 256+16C).
 // Roles (384 threads): warp 0 TMA producer, warp 1 stem MMA issuer, warp 2 TMEM allocator + similarity MMA
 // issuer (one elected thread each: two independent instruction streams into the one tensor pipe, so the
-// barrier polls of one never starve it), warps 4..7 stem epilogue, warps 8..11 converters.
+// barrier polls of one never starve it), warps 4..7 stem epilogue (bf16 results staged in swizzled shared
+// memory, one TMA store per warp and step), warps 8..11 converters.
+//
+// Budget (C = 12, 150 x 1500): the kernel is bound by the shared-memory port (128 B/clk), which every
+// operand read of an SS-mode MMA goes through.  Per step (2 output rows x 60 px): stem MMA operands
+// 21 x 8 KB = 168 KB, similarity MMA operands 55 KB, TMA operand writes 55 KB, converter stores 16 KB,
+// epilogue staging 16 KB written + 16 KB read by the TMA store: ~340 KB = 2.7 k cycles, against 1.8 k
+// cycles of tensor math (21 x 64 + 12 x 39.5).  Measured: ~2.5 k cycles per step.
 #include "kws_common.cuh"
 #include "../../include/kws_b200.h"
 
@@ -167,7 +176,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
   uint8_t* s_w = s_ops + G_NS * G_STAGE;          // G_W_BYTES
   uint8_t* s_ostage = s_w + G_W_BYTES;            // G_OUT_STAGE (4 x 4 KB, each 1024-aligned)
   uint8_t* s_ring = s_ostage + G_OUT_STAGE;       // G_RING_BYTES
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + G_RING_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + G_RING_BYTES - 64);  // from the last block's (unused) bank pad on
   uint64_t* ofull = bars;                 // [G_NS] TMA -> MMA (similarity operands)
   uint64_t* oempty = ofull + G_NS;        // [G_NS] MMA commit -> TMA
   uint64_t* sfull = oempty + G_NS;        // [G_NPAIR] MMA commit -> converters (similarity tiles of a layer pair ready)
@@ -273,8 +282,11 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
           for (int st = 0; st < stages_per_chunk; ++st) {
             const int c = st / p.nkb, kb = st - c * p.nkb;
             // the converters have pulled the previous chunk's tiles of this layer pair out of TMEM
+            if (st == 0) KWS_TRACE(2, g, 2);
             if (kb == 0 && (c & 1) == 0) mbar_wait(&sempty[c >> 1], (g & 1) ^ 1, 500 + (c >> 1));
+            if (st == 0) KWS_TRACE(2, g, 3);
             mbar_wait(&ofull[o_stage], o_phase, 300 + o_stage);
+            if (st == 0) KWS_TRACE(2, g, 4);
             tc_fence_after();
             const uint32_t d = G_TMEM_SIM + c * 16;  // TMEM base is 0 (checked at start)
             const uint32_t sa = ops_u32 + o_stage * G_STAGE;
@@ -287,6 +299,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
             if (++o_stage == G_NS) o_stage = 0, o_phase ^= 1;
             // layer pair complete (or last layer of an odd C): hand its tiles to the converters
             if (kb == p.nkb - 1 && ((c & 1) == 1 || c == p.C - 1)) umma_commit(&sfull[c >> 1]);
+            if (st == stages_per_chunk - 1) KWS_TRACE(2, g, 5);
           }
         }
       }
@@ -532,7 +545,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
     // ===================== converters: TMEM similarity rows -> fp16 ring =====================
     // A whole chunk (4 quanta x 4 rows x C layers) is pulled out of TMEM and packed to fp16 registers as soon
     // as its MMAs retire, so the single similarity region is handed back for the next chunk at once; the packed
-    // rows then enter the ring at the pace the stem frees slots.
+    // rows then enter the ring at the pace the stem frees slots (quantum P is released after kernel row 3 of step P).
     const int q4 = warp & 3;
     const int x = q4 * 32 + lane;  // pixel of the 128-wide input window
     uint8_t* dst_px = s_ring + (x & 1) * G_BLOCK + (x >> 1) * 16;
@@ -626,7 +639,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
   }
 }
 
-constexpr size_t G_SMEM = (size_t)G_NS * G_STAGE + G_W_BYTES + G_OUT_STAGE + G_RING_BYTES + G_NBAR * 8 + 16 + G_OC * 4;
+constexpr size_t G_SMEM = (size_t)G_NS * G_STAGE + G_W_BYTES + G_OUT_STAGE + G_RING_BYTES - 64 + G_NBAR * 8 + 16 + G_OC * 4;
 static_assert(G_SMEM <= 232448, "fused kernel exceeds the 227 KB shared-memory limit");
 
 // Fused-kernel weight layout: [di 7][m n_mma][chunk 2][n 128][e 8] fp16, BN scale folded.
@@ -665,6 +678,9 @@ __global__ void pack_stem_fused_kernel(const float* __restrict__ w, const float*
 using namespace kws;
 
 static long long* g_fused_dbg = nullptr;
+static int g_fused_grid_limit = 0;
+// development aid: cap the number of CTAs (to separate per-SM limits from chip-wide L2 limits)
+extern "C" void kws_debug_set_fused_grid_limit(int n) { g_fused_grid_limit = n; }
 
 // development aid (not part of the public header): device buffer [148][8] receiving the issuer's cycle counters
 extern "C" void kws_debug_set_fused_counters(long long* dev_buf) { g_fused_dbg = dev_buf; }
@@ -767,6 +783,7 @@ extern "C" int kws_sim_stem_range(const void* kwd_n, const void* utt_n, int C, i
   long long grid = p.num_items;
   const int sms = sm_count();
   if (grid > sms) grid = sms;
+  if (g_fused_grid_limit > 0 && grid > g_fused_grid_limit) grid = g_fused_grid_limit;
   p.dbg = g_fused_dbg;
   kern<<<(int)grid, G_THREADS, G_SMEM, (cudaStream_t)stream>>>(mu, mk, mo_lo, mo_hi, p);
   KWS_CUDA(cudaGetLastError());

@@ -16,6 +16,9 @@ ops.sim_stem(kn, un, wp, bias, ops.STEM_OUT_NHWC_BF16, out=out)
 TS = 640
 buf = torch.zeros(148 * 32 + 4 * TS * 8, dtype=torch.int64, device=dev)
 lib = _lib.load()
+if len(sys.argv) > 1:
+    lib.kws_debug_set_fused_grid_limit(int(sys.argv[1]))
+    print('grid limit', sys.argv[1])
 lib.kws_debug_set_fused_counters.argtypes = [ctypes.c_void_p]
 lib.kws_debug_set_fused_counters(buf.data_ptr())
 ops.sim_stem(kn, un, wp, bias, ops.STEM_OUT_NHWC_BF16, out=out)
@@ -34,6 +37,6 @@ for s in range(2 * nP, 5 * nP):  # items 2..4 of CTA 0 (steady state)
     prev_ret = e[0]
     print(f"{s:4d} P={s % nP:2d} | {r[0]:8d} +{r[1]-r[0]:5d} +{r[2]-r[1]:5d} +{r[3]-r[2]:5d} +{r[4]-r[3]:5d} +{r[5]-r[4]:5d} +{r[6]-r[5]:5d} | "
           f"{e[0]:8d} +{e[1]-e[0]:5d} +{e[2]-e[1]:5d} | len {iss[s+1,0]-iss[s,0]:5d} gap {gap:5d}")
-print("chunk | sfull_seen pulled(+)    quantum | slot_free stored(+)")
+print("chunk | sim issuer: start, +sempty0 wait, +ofull wait, last stage issued(+) | converter: first seen, pulled(+) | quanta: slot_free stored(+)")
 for c in range(20, 32):
-    print(f"chunk {c}: {chk[c,0]-t0:8d} +{chk[c,1]-chk[c,0]:5d}   " + "  ".join(f"q{4*c+j}: {qua[4*c+j,0]-t0:8d} +{qua[4*c+j,1]-qua[4*c+j,0]:4d}" for j in range(4)))
+    print(f"chunk {c}: sim {chk[c,2]-t0:8d} +{chk[c,3]-chk[c,2]:5d} +{chk[c,4]-chk[c,3]:5d} +{chk[c,5]-chk[c,4]:5d} | conv {chk[c,0]-t0:8d} +{chk[c,1]-chk[c,0]:5d}   " + "  ".join(f"q{4*c+j}: {qua[4*c+j,0]-t0:8d} +{qua[4*c+j,1]-qua[4*c+j,0]:4d}" for j in range(4)))
