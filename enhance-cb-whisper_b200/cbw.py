@@ -1,0 +1,135 @@
+"""Config #4: the original CB-Whisper keyword spotter (12-channel ResNet-50 on
+bilinearly resized cosine-similarity images), B200 path.
+
+Mirrors the two reference pieces that make up this variant of the hot path:
+
+* ``CBWhisper._calculate_cosine_similarity_matrices_`` (src/model/cb_whisper.py:189-210;
+  dataset twin src/data/dataset.py:311-317): per keyword
+  ``matmul(kwd_hs [C,Tk_i,D], utt_hs^T [S,C,D,Tu]) -> [S,C,Tk_i,Tu]`` on pre-normalised hidden
+  states, then ``torchvision resize(..., (150, 750), antialias=False)``;
+* the consumer ``KWSModel.forward(input_features [G,12,150,750])`` of src/model/model.py:78-93
+  (ResNet stem + body + head) and the ``argmax(logits) == 1`` detection rule of
+  src/model/cb_whisper.py:128.
+
+Here the ragged keywords are zero-padded into one resident fp16 bank, all keyword x segment
+similarities run through the tcgen05 GEMM (``kws_sim``), one resize kernel produces the fp16
+classifier input (``kws_resize_bilinear``) and the stem runs in ``kws_stem``; the ResNet body and
+head are the unmodified HuggingFace / torch modules.  CUDA only, inference only.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+from .model import run_body
+
+
+def pack_keywords(kwd_list: Sequence[torch.Tensor], device: torch.device, multiple: int = 16):
+    """Ragged pre-normalised keywords [C, Tk_i, D] -> (fp16 operand bank [C, K, Tkp, D], int32 lengths [K]).
+    Rows beyond a keyword's length are zero (they produce zero similarity and are never sampled by the
+    resize)."""
+    if len(kwd_list) == 0:
+        raise ops.KWSError("empty keyword list")
+    C, _, D = kwd_list[0].shape
+    lens = [int(k.shape[1]) for k in kwd_list]
+    if min(lens) < 1:
+        raise ops.KWSError("keywords need at least one frame")
+    Tkp = (max(lens) + multiple - 1) // multiple * multiple
+    bank = torch.zeros((len(kwd_list), C, Tkp, D), dtype=torch.float32, device=device)
+    for i, k in enumerate(kwd_list):
+        if k.shape[0] != C or k.shape[2] != D:
+            raise ops.KWSError(f"keyword {i} has shape {tuple(k.shape)}, expected [{C}, T, {D}]")
+        bank[i, :, : lens[i]] = k.to(device=device, dtype=torch.float32)
+    # operands are already unit vectors (src/utils.py:195); normalize_rows re-normalises (a no-op up to
+    # rounding), zeroes nothing (mask None) and casts to the layer-major fp16 layout
+    kwd_n = ops.normalize_rows(bank, list(range(C)), None)
+    return kwd_n, torch.tensor(lens, dtype=torch.int32, device=device)
+
+
+def similarity_images(kwd_list: Sequence[torch.Tensor], utt_hs: torch.Tensor, size: Tuple[int, int] = (150, 750),
+                      want_f32: bool = True, want_f16: bool = False):
+    """Replacement of ``_calculate_cosine_similarity_matrices_``.
+
+    kwd_list: K ragged keywords [C, Tk_i, D]; utt_hs: [S, C, Tu, D] (both L2-normalised over D).
+    Returns (fp32 [K, S, C, size0, size1] | None, fp16 [K, S, C, size0, pitch] | None).  (The reference
+    returns a per-segment list of [K, C, size0, size1]; index the result with ``[:, s]``.)"""
+    if not utt_hs.is_cuda:
+        raise ops.KWSError("utt_hs must be a CUDA tensor (the kws_b200 path has no CPU fallback)")
+    dev = utt_hs.device
+    S, C, Tu, D = utt_hs.shape
+    kwd_n, lens = pack_keywords(kwd_list, dev)
+    utt_n = ops.normalize_rows(utt_hs.float().contiguous(), list(range(C)), None)
+    K = kwd_n.shape[1]
+    # bound the fp32 intermediate [kb, S, C, Tkp, Tu]
+    per_kw = S * C * kwd_n.shape[2] * Tu * 4
+    kb = max(1, min(K, (2 << 30) // max(per_kw, 1), 65535 // (S * C)))
+    o32, o16 = [], []
+    for k0 in range(0, K, kb):
+        k1 = min(K, k0 + kb)
+        f32, _ = ops.sim(kwd_n[:, k0:k1].contiguous(), utt_n, want_f32=True, want_f16=False)
+        a, b = ops.resize_bilinear(f32, lens[k0:k1].contiguous(), size, want_f32=want_f32, want_f16=want_f16)
+        o32.append(a)
+        o16.append(b)
+    cat = lambda xs: (xs[0] if len(xs) == 1 else torch.cat(xs)) if xs[0] is not None else None
+    return cat(o32), cat(o16)
+
+
+class CBWKeywordSpotterB200:
+    """12-channel ResNet classifier on resized similarity images: the B200 twin of the original
+    ``KWSModel`` (src/model/model.py:17-93) as driven by ``CBWhisper.keyword_spotting``
+    (src/model/cb_whisper.py:110-128).  ``resnet`` is a module with the reference wrapper's attribute names
+    (``feature_extractor``, ``classifier``), e.g. ``enhance_cb_whisper_b200.Resnet(12, 2)`` or the
+    reference's own ``model.resnet.Resnet`` carrying a trained checkpoint."""
+
+    def __init__(self, resnet: torch.nn.Module, size: Tuple[int, int] = (150, 750), body_dtype: str = "float32"):
+        self.resnet = resnet.eval()
+        self.size = tuple(size)
+        self.body_dtype = body_dtype
+        self._packed = None
+        self._lowp = None
+
+    def _weights(self, device):
+        if self._packed is None or self._packed[0].device != device:
+            emb = self.resnet.feature_extractor.embedder.embedder
+            self._packed = ops.pack_stem_weights(emb.convolution.weight.to(device), emb.normalization.weight.to(device),
+                                                 emb.normalization.bias.to(device),
+                                                 emb.normalization.running_mean.to(device),
+                                                 emb.normalization.running_var.to(device))
+        return self._packed
+
+    def _body(self, st):
+        if self.body_dtype == "float32":
+            return run_body(self.resnet, st)
+        if self._lowp is None:
+            import copy
+
+            m = copy.deepcopy(self.resnet).to(dtype=torch.bfloat16, memory_format=torch.channels_last)
+            m.classifier.float()
+            self._lowp = m.eval()
+        return run_body(self._lowp, st)
+
+    @torch.no_grad()
+    def logits(self, kwd_list: Sequence[torch.Tensor], utt_hs: torch.Tensor, max_pairs: int = 128) -> torch.Tensor:
+        """-> logits fp32 [K, S, 2] for every keyword x segment."""
+        dev = utt_hs.device
+        _, f16 = similarity_images(kwd_list, utt_hs, self.size, want_f32=False, want_f16=True)
+        K, S = f16.shape[:2]
+        wp, bias = self._weights(dev)
+        lowp = self.body_dtype != "float32"
+        flat = f16.view(K * S, *f16.shape[2:])
+        out = torch.empty((K * S, 2), dtype=torch.float32, device=dev)
+        for p0 in range(0, K * S, max_pairs):
+            p1 = min(K * S, p0 + max_pairs)
+            st = ops.stem(flat[p0:p1], self.size[1], wp, bias,
+                          ops.STEM_OUT_NHWC_BF16 if lowp else ops.STEM_OUT_NCHW_F32)
+            out[p0:p1] = self._body(st).float()
+        return out.view(K, S, 2)
+
+    @torch.no_grad()
+    def detect(self, kwd_list: Sequence[torch.Tensor], utt_hs: torch.Tensor) -> List[List[int]]:
+        """Per segment, the indices of the keywords with ``argmax(logits) == 1`` (cb_whisper.py:128)."""
+        lg = self.logits(kwd_list, utt_hs)
+        hit = lg.argmax(dim=-1) == 1  # [K,S]
+        return [torch.nonzero(hit[:, s]).flatten().tolist() for s in range(hit.shape[1])]

@@ -244,6 +244,39 @@ __global__ void cast16_kernel(const float* __restrict__ s, uint16_t* __restrict_
 }
 
 // ---------------------------------------------------------------------------
+// bilinear resize of similarity images (config #4, the original CB-Whisper classifier):
+// F.interpolate(mode="bilinear", align_corners=False, antialias=False) semantics, i.e.
+// src = scale * (dst + 0.5) - 0.5 clamped at 0, neighbours (i0, min(i0 + 1, n - 1)).
+// in  fp32 [K, U, C, Hs, Ws]; rows >= src_h[k] of keyword k are padding and never read
+// out fp16 [K, U, C, Ho, pitch16] (stem input) and/or fp32 [K, U, C, Ho, Wo]
+// One block row per (image, output row); threads run along the output columns.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) resize_bilinear_kernel(const float* __restrict__ in, const int32_t* __restrict__ src_h,
+                                                              int U, int C, int Hs, int Ws, int Ho, int Wo, int pitch16,
+                                                              float* __restrict__ out32, __half* __restrict__ out16) {
+  const long long img = blockIdx.y;  // (k * U + u) * C + c
+  const int k = (int)(img / ((long long)U * C));
+  const int h = src_h ? min(max(src_h[k], 1), Hs) : Hs;
+  const float sy = (float)h / (float)Ho, sx = (float)Ws / (float)Wo;
+  const float* src = in + img * (long long)Hs * Ws;
+  for (int i = blockIdx.x; i < Ho; i += gridDim.x) {
+    const float fy = fmaxf(sy * ((float)i + 0.5f) - 0.5f, 0.f);
+    const int y0 = min((int)fy, h - 1), y1 = y0 + (y0 < h - 1 ? 1 : 0);
+    const float ly1 = fy - (float)y0, ly0 = 1.f - ly1;
+    const float* r0 = src + (long long)y0 * Ws;
+    const float* r1 = src + (long long)y1 * Ws;
+    for (int j = threadIdx.x; j < Wo; j += blockDim.x) {
+      const float fx = fmaxf(sx * ((float)j + 0.5f) - 0.5f, 0.f);
+      const int x0 = min((int)fx, Ws - 1), x1 = x0 + (x0 < Ws - 1 ? 1 : 0);
+      const float lx1 = fx - (float)x0, lx0 = 1.f - lx1;
+      const float v = ly0 * (lx0 * __ldg(r0 + x0) + lx1 * __ldg(r0 + x1)) + ly1 * (lx0 * __ldg(r1 + x0) + lx1 * __ldg(r1 + x1));
+      if (out32) out32[(img * Ho + i) * (long long)Wo + j] = v;
+      if (out16) out16[(img * Ho + i) * (long long)pitch16 + j] = __float2half_rn(v);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // scores + top-k
 // ---------------------------------------------------------------------------
 __global__ void scores_kernel(const float* __restrict__ logits, const float* __restrict__ hw, size_t n,
@@ -339,6 +372,27 @@ int kws_temporal(const float* proj, int C, int B, int T, int P, const float* w_f
   temporal_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(proj, C, B, T, P, T2, w_folded, b_folded, mask, eps,
                                                             (__half*)out_f16);
   KWS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int kws_resize_bilinear(const float* feat_f32, const int32_t* src_h, int K, int U, int C, int Hs, int Ws, int Ho, int Wo,
+                        float* out_f32, void* out_f16, int pitch16, void* stream) {
+  KWS_CHECK_ARG(feat_f32 && (out_f32 || out_f16), "resize: null pointer");
+  KWS_CHECK_ARG(K > 0 && U > 0 && C > 0 && Hs > 0 && Ws > 0 && Ho > 0 && Wo > 0, "resize: non-positive dimension");
+  KWS_CHECK_ARG(!out_f16 || pitch16 >= Wo, "resize: pitch16=%d < Wo=%d", pitch16, Wo);
+  KWS_CHECK_ARG((long long)U * C <= 65535, "resize: U*C=%lld images per keyword exceed one launch", (long long)U * C);
+  // gridDim.y <= 65535: launch whole keywords at a time
+  const int kb = (int)(65535ll / ((long long)U * C));
+  for (int k0 = 0; k0 < K; k0 += kb) {
+    const int nk = K - k0 < kb ? K - k0 : kb;
+    const long long i0 = (long long)k0 * U * C;
+    dim3 grid(Ho < 32 ? Ho : 32, (unsigned)(nk * U * C));
+    resize_bilinear_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        feat_f32 + i0 * (long long)Hs * Ws, src_h ? src_h + k0 : nullptr, U, C, Hs, Ws, Ho, Wo, pitch16,
+        out_f32 ? out_f32 + i0 * (long long)Ho * Wo : nullptr,
+        out_f16 ? reinterpret_cast<__half*>(out_f16) + i0 * (long long)Ho * pitch16 : nullptr);
+    KWS_CUDA(cudaGetLastError());
+  }
   return 0;
 }
 

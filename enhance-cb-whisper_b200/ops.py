@@ -276,6 +276,24 @@ def sim_stem(kwd_n: torch.Tensor, utt_n: torch.Tensor, w_fused: torch.Tensor, bi
     return view
 
 
+def resize_bilinear(feat_f32: torch.Tensor, src_h: Optional[torch.Tensor], size: Tuple[int, int],
+                    want_f32: bool = False, want_f16: bool = True):
+    """feat fp32 [K,U,C,Hs,Ws] (+ src_h int32 [K]: valid rows per keyword) -> bilinear (align_corners=False)
+    resize to ``size``: (fp32 [K,U,C,Ho,Wo] | None, fp16 [K,U,C,Ho,pitch] | None)."""
+    lib = _lib.load()
+    K, U, Cc, Hs, Ws = feat_f32.shape
+    Ho, Wo = size
+    pitch = pitch_for(Wo)
+    o32 = torch.empty((K, U, Cc, Ho, Wo), dtype=torch.float32, device=feat_f32.device) if want_f32 else None
+    o16 = torch.empty((K, U, Cc, Ho, pitch), dtype=torch.float16, device=feat_f32.device) if want_f16 else None
+    if src_h is not None and (src_h.dtype != torch.int32 or src_h.numel() != K):
+        raise KWSError("src_h must be int32 [K]")
+    check(lib.kws_resize_bilinear(_cuda(feat_f32, "feat_f32", torch.float32), _cuda(src_h, "src_h", torch.int32), K, U,
+                                  Cc, Hs, Ws, Ho, Wo, _cuda(o32, "out_f32"), _cuda(o16, "out_f16"), pitch, _stream()),
+          "kws_resize_bilinear", launches=(K + max(1, 65535 // (U * Cc)) - 1) // max(1, 65535 // (U * Cc)))
+    return o32, o16
+
+
 # ---- scores ------------------------------------------------------------------------
 def scores(logits: torch.Tensor, hotword_mask: Optional[torch.Tensor], threshold: float):
     """logits fp32 [n,2] -> (scores fp32 [n], detections uint8 [n])"""

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define KWS_ABI_VERSION 3
+#define KWS_ABI_VERSION 4
 
 /* 16-bit operand formats (same encoding as the tcgen05 kind::f16 descriptor) */
 #define KWS_F16 0  /* IEEE half: 10-bit mantissa; for L2-normalised data and sane weights */
@@ -169,6 +169,17 @@ int kws_sim_stem_supported(int C, int Tk, int Tu, int Dk);
 int kws_sim_stem_range(const void* kwd_n, const void* utt_n, int C, int K, int U, int Tk, int Tu, int Dk,
                        int pair_mode, int k0, int nk, int u0, int nu, const void* w_fused, const float* bias,
                        int out_mode, void* out, void* stream);
+
+/* Config #4 (original CB-Whisper classifier): bilinear resize of the layer-wise similarity images of
+ * ragged keywords to the classifier's fixed input size (replaces torchvision resize(..., antialias=False)
+ * == F.interpolate(bilinear, align_corners=False), src/model/cb_whisper.py:208; dataset twin
+ * src/data/dataset.py:312-317).
+ *   feat_f32 fp32 [K,U,C,Hs,Ws] from kws_sim (keywords zero-padded to Hs frames)
+ *   src_h DEVICE int32 [K]: valid frames of each keyword (NULL: all Hs)
+ *   out_f32 fp32 [K,U,C,Ho,Wo] or NULL; out_f16 fp16 [K,U,C,Ho,pitch16] or NULL (kws_stem input)
+ *   Requires U*C <= 65535 (whole keywords per launch).                                           */
+int kws_resize_bilinear(const float* feat_f32, const int32_t* src_h, int K, int U, int C, int Hs, int Ws, int Ho, int Wo,
+                        float* out_f32, void* out_f16, int pitch16, void* stream);
 
 /* ---- scores ---------------------------------------------------------------- */
 

@@ -278,3 +278,66 @@ def test_topk_matches_torch_with_index_tiebreak(ops, cuda_dev, n, U, k):
     order = torch.argsort(-sc.double() - 0.0, dim=0, stable=True)[:k]  # stable: lower index first on ties
     assert torch.equal(v, torch.gather(sc, 0, order))
     assert torch.equal(i.long(), order + 100)
+
+
+# ---- config #4: similarity + bilinear resize (original CB-Whisper classifier) ---------------------
+@pytest.mark.parametrize("K,U,Cc,Hs,Ws,size", [(3, 2, 2, 16, 40, (9, 20)), (2, 1, 3, 32, 150, (150, 75)),
+                                               (4, 1, 1, 16, 31, (7, 50))])
+def test_resize_bilinear_matches_interpolate(ops, cuda_dev, K, U, Cc, Hs, Ws, size):
+    g = gen(cuda_dev)
+    x = torch.randn(K, U, Cc, Hs, Ws, generator=g, device=cuda_dev)
+    h = torch.randint(1, Hs + 1, (K,), generator=g, device=cuda_dev, dtype=torch.int32)
+    o32, o16 = ops.resize_bilinear(x, h, size, want_f32=True, want_f16=True)
+    for k in range(K):
+        exp = torch.nn.functional.interpolate(x[k, :, :, : int(h[k])].flatten(0, 1)[None], size=size, mode="bilinear",
+                                              align_corners=False, antialias=False)[0].view(U, Cc, *size)
+        assert maxerr(o32[k], exp) <= 1e-5
+        assert maxerr(o16[k][..., : size[1]], exp) <= 2e-3 * max(1.0, exp.abs().max().item())
+    # no length table: every source row is valid
+    o32b, _ = ops.resize_bilinear(x, None, size, want_f32=True, want_f16=False)
+    expb = torch.nn.functional.interpolate(x.flatten(0, 2)[None], size=size, mode="bilinear", align_corners=False)[0]
+    assert maxerr(o32b.flatten(0, 2), expb) <= 1e-5
+
+
+def test_cbw_similarity_images_match_oracle(built_lib, cuda_dev):
+    """B200 config-#4 path == restated cb_whisper.py:189-210 (ragged keywords, matmul, bilinear resize)."""
+    from enhance_cb_whisper_b200 import cbw
+
+    g = torch.Generator().manual_seed(11)
+    Cc, D, Tu, S = 3, 128, 140, 2
+    kwd_list = [torch.nn.functional.normalize(torch.randn(Cc, t, D, generator=g), dim=-1) for t in (5, 17, 33, 1)]
+    utt = torch.nn.functional.normalize(torch.randn(S, Cc, Tu, D, generator=g), dim=-1)
+    exp = O.cbw_similarity_resized(kwd_list, utt, size=(30, 70))  # [K,S,C,30,70]
+    got32, got16 = cbw.similarity_images([k.to(cuda_dev) for k in kwd_list], utt.to(cuda_dev), size=(30, 70),
+                                         want_f32=True, want_f16=True)
+    assert got32.shape == exp.shape
+    assert maxerr(got32.cpu(), exp) <= 2e-3
+    assert maxerr(got16[..., :70].cpu(), exp) <= 2e-3
+
+
+def test_cbw_keyword_spotter_logits_and_detections(built_lib, cuda_dev):
+    """12-channel classifier on the resized images: logits within 2e-3 of the reference arithmetic
+    (src/model/model.py:78-93 on the images of cb_whisper.py:189-210), same argmax detections."""
+    from enhance_cb_whisper_b200 import Resnet, cbw
+
+    torch.manual_seed(5)
+    g = torch.Generator().manual_seed(12)
+    Cc, D, Tu, S, size = 12, 64, 100, 2, (30, 50)
+    resnet = Resnet(Cc, 2, "resnet-18").eval()
+    bn = resnet.feature_extractor.embedder.embedder.normalization
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(64, generator=g) + 0.5), bn.bias.copy_(torch.randn(64, generator=g) * 0.1)
+        bn.running_mean.copy_(torch.randn(64, generator=g) * 0.1), bn.running_var.copy_(torch.rand(64, generator=g) + 0.5)
+    kwd_list = [torch.nn.functional.normalize(torch.randn(Cc, t, D, generator=g), dim=-1) for t in (9, 21, 14)]
+    utt = torch.nn.functional.normalize(torch.randn(S, Cc, Tu, D, generator=g), dim=-1)
+    with torch.inference_mode():
+        imgs = O.cbw_similarity_resized(kwd_list, utt, size=size)  # [K,S,C,h,w]
+        exp = resnet(imgs.flatten(0, 1)).view(len(kwd_list), S, 2)
+    sp = cbw.CBWKeywordSpotterB200(resnet.to(cuda_dev), size=size)
+    got = sp.logits([k.to(cuda_dev) for k in kwd_list], utt.to(cuda_dev))
+    assert maxerr(got.cpu(), exp) <= 2e-3
+    det = sp.detect([k.to(cuda_dev) for k in kwd_list], utt.to(cuda_dev))
+    exp_hit = exp.argmax(-1) == 1
+    margin = (exp[..., 1] - exp[..., 0]).abs().min().item()
+    if margin > 1e-2:
+        assert det == [torch.nonzero(exp_hit[:, s]).flatten().tolist() for s in range(S)]
