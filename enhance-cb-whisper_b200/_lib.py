@@ -12,7 +12,7 @@ import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libkws_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # constants of include/kws_b200.h
 F16, BF16 = 0, 1

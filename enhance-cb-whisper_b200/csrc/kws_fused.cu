@@ -93,7 +93,7 @@ constexpr int G_ACC_COLS = 128;                    // one stem accumulator: half
 constexpr int G_TMEM_SIM = 2 * G_ACC_COLS;         // similarity region starts at column 256
 constexpr int G_OUT_STAGE = 4 * 32 * 128;          // per epilogue warp: 32 pixels x 64 bf16 (SW128), source of its TMA stores
 constexpr int G_NPAIR = G_MAX_C / 2;                 // similarity tiles are handed over per pair of layers
-constexpr int G_NBAR = 2 * G_NS + 2 * G_NPAIR + 4 + 4 + 2 + 2;
+constexpr int G_NBAR = 2 * G_NS + 2 * G_NPAIR + 4 + 4 + 2 + 2 + 4;
 
 struct FusedParams {
   const uint4* w;     // fused stem weights (kws_pack_stem_fused)
@@ -102,6 +102,9 @@ struct FusedParams {
   int out_mode;
   int C, K, U, Tk, Tu, nkb, Ho, Wo, col_tiles;  // K, U: operand batch sizes (tensor-map extents)
   int k0, u0, nk, nu;  // scored sub-range: keywords [k0, k0+nk) x utterances [u0, u0+nu); out pair = (k-k0)*nu + (u-u0)
+  int c0;        // first layer of this pass in the operand banks (C layers [c0, c0+C) are processed)
+  int C_total;   // layers in the operand banks (tensor-map batch = layer * bank size + item)
+  int acc_mode;  // 0 single pass | 1 first pass: write fp16 partial sums | 2 middle: += | 3 last: +=, bias, ReLU, bf16
   int n_mma;     // stem MMAs per kernel row: 2 (C <= 8) or 3
   int nP;        // stem steps per item = ceil(Ho / 2)
   int nQ;        // quanta (4 input rows) converted per item = nP + 2
@@ -141,6 +144,17 @@ __device__ __forceinline__ uint32_t relu_bf16x2(uint64_t v) {  // {lo, hi} fp32 
   asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
   return r;
+}
+
+__device__ __forceinline__ uint32_t f16x2_of(uint64_t v) {  // {lo, hi} fp32 -> fp16x2 (partial sums between passes)
+  uint32_t lo, hi, r;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  return r;
+}
+__device__ __forceinline__ uint64_t f32x2_of_f16x2(uint32_t h) {
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h));
+  return pack_b64(__float_as_uint(f.x), __float_as_uint(f.y));
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -185,6 +199,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
   uint64_t* qempty = qfull + 4;           // [4] MMA commit -> converters
   uint64_t* afull = qempty + 4;           // [2] MMA commit -> epilogue (stem accumulator ready)
   uint64_t* aempty = afull + 2;           // [2] epilogue -> MMA
+  uint64_t* pload = aempty + 2;           // [4] TMA load of the previous pass's partial sums -> epilogue warp
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + G_NBAR);
   float* s_bias = reinterpret_cast<float*>(bars + G_NBAR + 2);  // [64]; L1 is carved down to nothing, keep it out of L2
 
@@ -228,6 +243,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
     for (int s = 0; s < 4; ++s) {
       mbar_init(&qfull[s], 128);
       mbar_init(&qempty[s], 1);
+      mbar_init(&pload[s], 1);
     }
     fence_barrier_init();
   }
@@ -259,8 +275,8 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
               mbar_wait(&oempty[stage], phase ^ 1, 100 + stage);
               uint8_t* sa = s_ops + stage * G_STAGE;
               mbar_arrive_expect_tx(&ofull[stage], G_STAGE);
-              tma_load_3d(&map_utt, &ofull[stage], sa, kb * 64, jbase, c * p.U + w.u);
-              tma_load_3d(&map_kwd, &ofull[stage], sa + G_A_BYTES, kb * 64, 16 * n - 3, c * p.K + w.kw);
+              tma_load_3d(&map_utt, &ofull[stage], sa, kb * 64, jbase, (p.c0 + c) * p.U + w.u);
+              tma_load_3d(&map_kwd, &ofull[stage], sa + G_A_BYTES, kb * 64, 16 * n - 3, (p.c0 + c) * p.K + w.kw);
               if (++stage == G_NS) stage = 0, phase ^= 1;
             }
           }
@@ -402,6 +418,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
     float* mbox1 = mbox0 + 64;
     const CUtensorMap* my_map = lo_warp ? &map_out_lo : &map_out_hi;
     uint32_t acc_seq = 0;
+    uint32_t pl_seq = 0;  // partial-sum tiles loaded so far by this warp (phase of pload[q])
     long long te_wait = 0, te_ld = 0, te_rest = 0;
     long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (long long it = blockIdx.x; it < p.num_items; it += gridDim.x) {
@@ -419,6 +436,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
         const uint32_t t_row = tmem_base + acc * G_ACC_COLS + ((uint32_t)(q * 32) << 16);
         const int oi = 2 * P + row_sel;
         const bool ok = col_ok && oi < p.Ho;
+        const bool tile_ok = oi < p.Ho && w.ct * G_TILE_OJ + (q & 1) * 32 < p.Wo;  // this warp stores a tile this step
         float* o32 = nullptr;
         long long oc_stride = 0;
         if (!nhwc) {
@@ -436,7 +454,19 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
           }
           if (grp == 0) {
             // the previous step's TMA store must have read this warp's staging buffer before it is reused
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (lane == 0) {
+              asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              if (nhwc && p.acc_mode >= 2 && tile_ok) {
+                // partial sums of the previous channel-group pass: same tile, same staging layout
+                mbar_arrive_expect_tx(&pload[q], (lo_warp ? 32u : (uint32_t)(G_TILE_OJ - 32)) * 128u);
+                asm volatile(
+                    "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+                    "%6}], [%2];" ::"r"(smem_u32(my_stage)),
+                    "l"(reinterpret_cast<uint64_t>(my_map)), "r"(smem_u32(&pload[q])), "r"(0),
+                    "r"(w.ct * G_TILE_OJ + (q & 1) * 32), "r"(oi), "r"((int)w.pair)
+                    : "memory");
+              }
+            }
             __syncwarp();
           }
           tmem_ld_wait();
@@ -478,23 +508,39 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
           for (int h = 0; h < 2; ++h) {
             const int ch = grp * 2 + h;
             if constexpr (nhwc) {
+              const bool with_bias = p.acc_mode == 0 || p.acc_mode == 3;  // single or last channel-group pass
+              const bool add_prev = p.acc_mode >= 2 && tile_ok;
+              uint8_t* c0p = srow + (((2 * ch) ^ (lane & 7)) << 4);
+              uint8_t* c1p = srow + (((2 * ch + 1) ^ (lane & 7)) << 4);
+              uint32_t prev[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+              if (add_prev) {  // fp16 partial sums of the previous passes, TMA-loaded into the staging tile
+                if (grp == 0 && h == 0) mbar_wait(&pload[q], pl_seq & 1, 950 + q);
+                const uint4 a = *reinterpret_cast<const uint4*>(c0p), b = *reinterpret_cast<const uint4*>(c1p);
+                prev[0] = a.x, prev[1] = a.y, prev[2] = a.z, prev[3] = a.w;
+                prev[4] = b.x, prev[5] = b.y, prev[6] = b.z, prev[7] = b.w;
+              }
               uint32_t o[8];
 #pragma unroll
               for (int e = 0; e < 16; e += 4) {
-                const float4 b4 = *reinterpret_cast<const float4*>(s_bias + ch * 16 + e);
-                const uint64_t s0 = add_f32x2(add_f32x2(pack_b64(va[h][e], va[h][e + 1]), pack_b64(vb[h][e], vb[h][e + 1])),
-                                              pack_b64(__float_as_uint(b4.x), __float_as_uint(b4.y)));
-                const uint64_t s1 =
-                    add_f32x2(add_f32x2(pack_b64(va[h][e + 2], va[h][e + 3]), pack_b64(vb[h][e + 2], vb[h][e + 3])),
-                              pack_b64(__float_as_uint(b4.z), __float_as_uint(b4.w)));
-                o[e >> 1] = relu_bf16x2(s0);
-                o[(e >> 1) + 1] = relu_bf16x2(s1);
+                uint64_t s0 = add_f32x2(pack_b64(va[h][e], va[h][e + 1]), pack_b64(vb[h][e], vb[h][e + 1]));
+                uint64_t s1 = add_f32x2(pack_b64(va[h][e + 2], va[h][e + 3]), pack_b64(vb[h][e + 2], vb[h][e + 3]));
+                if (with_bias) {
+                  const float4 b4 = *reinterpret_cast<const float4*>(s_bias + ch * 16 + e);
+                  s0 = add_f32x2(s0, pack_b64(__float_as_uint(b4.x), __float_as_uint(b4.y)));
+                  s1 = add_f32x2(s1, pack_b64(__float_as_uint(b4.z), __float_as_uint(b4.w)));
+                }
+                if (add_prev) {
+                  s0 = add_f32x2(s0, f32x2_of_f16x2(prev[e >> 1]));
+                  s1 = add_f32x2(s1, f32x2_of_f16x2(prev[(e >> 1) + 1]));
+                }
+                o[e >> 1] = with_bias ? relu_bf16x2(s0) : f16x2_of(s0);
+                o[(e >> 1) + 1] = with_bias ? relu_bf16x2(s1) : f16x2_of(s1);
               }
               // 16-byte chunks 2ch, 2ch+1 of this pixel's 128-byte row, 128B swizzle (chunk ^ (row & 7));
               // rows 28..31 of the hi warp are idle pixel slots and hold the mailboxes: never written here
               if (lo_warp || lane < G_TILE_OJ - 32) {
-                *reinterpret_cast<uint4*>(srow + (((2 * ch) ^ (lane & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
-                *reinterpret_cast<uint4*>(srow + (((2 * ch + 1) ^ (lane & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+                *reinterpret_cast<uint4*>(c0p) = make_uint4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<uint4*>(c1p) = make_uint4(o[4], o[5], o[6], o[7]);
               }
             } else {
               float r[16];
@@ -519,9 +565,10 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
           tp[7] = f2;
         }
         if constexpr (nhwc) {
+          if (p.acc_mode >= 2 && tile_ok) ++pl_seq;
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0 && oi < p.Ho && w.ct * G_TILE_OJ + (q & 1) * 32 < p.Wo) {
+          if (lane == 0 && tile_ok) {
             asm volatile(
                 "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
                     reinterpret_cast<uint64_t>(my_map)),
@@ -650,8 +697,8 @@ static_assert(G_SMEM <= 232448, "fused kernel exceeds the 227 KB shared-memory l
 // taps dj > 6 and channels >= C are zero.
 __global__ void pack_stem_fused_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
                                        const float* __restrict__ beta, const float* __restrict__ mean,
-                                       const float* __restrict__ var, float eps, int C, int n_mma,
-                                       __half* __restrict__ wp, float* __restrict__ bias) {
+                                       const float* __restrict__ var, float eps, int C_total, int c_base, int C,
+                                       int n_mma, __half* __restrict__ wp, float* __restrict__ bias) {
   const int total = 7 * n_mma * 2 * 128 * 8;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int e = i & 7, n = (i >> 3) & 127, chunk = (i >> 10) & 1;
@@ -666,7 +713,8 @@ __global__ void pack_stem_fused_kernel(const float* __restrict__ w, const float*
       dj = chunk + 2 * (e >> 2) + 4 * half, ch = 8 + (e & 3);
     }
     float v = 0.f;
-    if (dj < 7 && ch < C) v = w[(((size_t)oc * C + ch) * 7 + di) * 7 + dj] * (gamma[oc] / sqrtf(var[oc] + eps));
+    if (dj < 7 && ch < C)
+      v = w[(((size_t)oc * C_total + c_base + ch) * 7 + di) * 7 + dj] * (gamma[oc] / sqrtf(var[oc] + eps));
     wp[i] = __float2half_rn(v);
   }
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -686,23 +734,39 @@ extern "C" void kws_debug_set_fused_grid_limit(int n) { g_fused_grid_limit = n; 
 extern "C" void kws_debug_set_fused_counters(long long* dev_buf) { g_fused_dbg = dev_buf; }
 
 static int fused_n_mma(int C) { return C <= 8 ? 2 : 3; }
+// C > 12 layers are processed in passes over channel groups of at most G_MAX_C layers; the passes chain their
+// partial sums through the output buffer itself (fp16, same tiles), the last one adds bias + ReLU -> bf16.
+constexpr int G_MAX_C_TOTAL = 64;
+static int fused_groups(int C) { return (C + G_MAX_C - 1) / G_MAX_C; }
+static int fused_group_layers(int C, int g) { return g < fused_groups(C) - 1 ? G_MAX_C : C - g * G_MAX_C; }
+static size_t fused_group_bytes(int Cg) { return (size_t)7 * fused_n_mma(Cg) * G_MMA_W_BYTES; }
 
 extern "C" size_t kws_stem_fused_weight_bytes(int C) {
-  return C > 0 && C <= G_MAX_C ? (size_t)7 * fused_n_mma(C) * G_MMA_W_BYTES : 0;
+  if (C <= 0 || C > G_MAX_C_TOTAL) return 0;
+  size_t n = 0;
+  for (int g = 0; g < fused_groups(C); ++g) n += fused_group_bytes(fused_group_layers(C, g));
+  return n;
 }
 
 extern "C" int kws_pack_stem_fused(const float* conv_w, const float* gamma, const float* beta, const float* mean,
                                    const float* var, float eps, int C, void* w_fused, float* bias, void* stream) {
   KWS_CHECK_ARG(conv_w && gamma && beta && mean && var && w_fused && bias, "pack_stem_fused: null pointer");
-  KWS_CHECK_ARG(C > 0 && C <= G_MAX_C, "pack_stem_fused: C=%d out of (0,%d]", C, G_MAX_C);
-  pack_stem_fused_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(conv_w, gamma, beta, mean, var, eps, C, fused_n_mma(C),
-                                                               (__half*)w_fused, bias);
-  KWS_CUDA(cudaGetLastError());
+  KWS_CHECK_ARG(C > 0 && C <= G_MAX_C_TOTAL, "pack_stem_fused: C=%d out of (0,%d]", C, G_MAX_C_TOTAL);
+  uint8_t* dst = reinterpret_cast<uint8_t*>(w_fused);
+  for (int g = 0; g < fused_groups(C); ++g) {
+    const int Cg = fused_group_layers(C, g);
+    pack_stem_fused_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(conv_w, gamma, beta, mean, var, eps, C, g * G_MAX_C, Cg,
+                                                                 fused_n_mma(Cg), (__half*)dst, bias);
+    KWS_CUDA(cudaGetLastError());
+    dst += fused_group_bytes(Cg);
+  }
   return 0;
 }
 
+// 1: fused kernel available for both output modes; 2: bf16 channels-last only (C > 12: multi-pass); 0: no
 extern "C" int kws_sim_stem_supported(int C, int Tk, int Tu, int Dk) {
-  return C > 0 && C <= G_MAX_C && Dk >= 64 && Dk % 64 == 0 && Tk > 0 && Tu > 0;
+  if (!(C > 0 && C <= G_MAX_C_TOTAL && Dk >= 64 && Dk % 64 == 0 && Tk > 0 && Tu > 0)) return 0;
+  return C <= G_MAX_C ? 1 : 2;
 }
 
 extern "C" int kws_sim_stem(const void* kwd_n, const void* utt_n, int C, int K, int U, int Tk, int Tu, int Dk,
@@ -719,7 +783,9 @@ extern "C" int kws_sim_stem_range(const void* kwd_n, const void* utt_n, int C, i
   KWS_CHECK_ARG(C > 0 && K > 0 && U > 0 && Tk > 0 && Tu > 0, "sim_stem: non-positive dimension");
   KWS_CHECK_ARG(k0 >= 0 && nk > 0 && k0 + nk <= K, "sim_stem: keyword range [%d,%d) outside [0,%d)", k0, k0 + nk, K);
   KWS_CHECK_ARG(u0 >= 0 && nu > 0 && u0 + nu <= U, "sim_stem: utterance range [%d,%d) outside [0,%d)", u0, u0 + nu, U);
-  KWS_CHECK_ARG(C <= G_MAX_C, "sim_stem: C=%d > %d layers (use kws_sim + kws_stem)", C, G_MAX_C);
+  KWS_CHECK_ARG(C <= G_MAX_C_TOTAL, "sim_stem: C=%d > %d layers", C, G_MAX_C_TOTAL);
+  KWS_CHECK_ARG(C <= G_MAX_C || out_mode == KWS_STEM_OUT_NHWC_BF16,
+                "sim_stem: C=%d > %d layers needs the bf16 channels-last output (multi-pass partial sums)", C, G_MAX_C);
   KWS_CHECK_ARG(Dk % 64 == 0 && Dk >= 64, "sim_stem: Dk=%d must be a multiple of 64", Dk);
   KWS_CHECK_ARG(pair_mode == KWS_PAIRS_ALL || pair_mode == KWS_PAIRS_DIAG, "sim_stem: bad pair_mode %d", pair_mode);
   KWS_CHECK_ARG(pair_mode == KWS_PAIRS_ALL || (U == K && k0 == u0 && nk == nu),
@@ -763,15 +829,14 @@ extern "C" int kws_sim_stem_range(const void* kwd_n, const void* utt_n, int C, i
       return e;
   }
   FusedParams p{};
-  p.w = reinterpret_cast<const uint4*>(w_fused);
   p.bias = bias;
   p.out = out;
   p.out_mode = out_mode;
-  p.C = C, p.K = K, p.U = U, p.Tk = Tk, p.Tu = Tu, p.nkb = Dk / 64;
+  p.K = K, p.U = U, p.Tk = Tk, p.Tu = Tu, p.nkb = Dk / 64;
   p.k0 = k0, p.u0 = u0, p.nk = nk, p.nu = nu;
-  p.n_mma = fused_n_mma(C);
-  p.Ho = (Tk + 1) / 2;
-  p.Wo = (Tu + 1) / 2;
+  p.C_total = C;
+  p.Ho = Ho;
+  p.Wo = Wo;
   p.col_tiles = (p.Wo + G_TILE_OJ - 1) / G_TILE_OJ;
   p.nP = (p.Ho + 1) / 2;
   p.nQ = p.nP + 2;
@@ -785,7 +850,18 @@ extern "C" int kws_sim_stem_range(const void* kwd_n, const void* utt_n, int C, i
   if (grid > sms) grid = sms;
   if (g_fused_grid_limit > 0 && grid > g_fused_grid_limit) grid = g_fused_grid_limit;
   p.dbg = g_fused_dbg;
-  kern<<<(int)grid, G_THREADS, G_SMEM, (cudaStream_t)stream>>>(mu, mk, mo_lo, mo_hi, p);
-  KWS_CUDA(cudaGetLastError());
+  const int n_groups = fused_groups(C);
+  const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(w_fused);
+  for (int g = 0; g < n_groups; ++g) {
+    const int Cg = fused_group_layers(C, g);
+    p.w = reinterpret_cast<const uint4*>(wsrc);
+    p.C = Cg;
+    p.c0 = g * G_MAX_C;
+    p.n_mma = fused_n_mma(Cg);
+    p.acc_mode = n_groups == 1 ? 0 : (g == 0 ? 1 : (g == n_groups - 1 ? 3 : 2));
+    kern<<<(int)grid, G_THREADS, G_SMEM, (cudaStream_t)stream>>>(mu, mk, mo_lo, mo_hi, p);
+    KWS_CUDA(cudaGetLastError());
+    wsrc += fused_group_bytes(Cg);
+  }
   return 0;
 }

@@ -140,9 +140,10 @@ class KWSEngine:
             for k0 in range(0, K, kb):
                 yield k0, min(K, k0 + kb), u0, min(U, u0 + ub)
 
-    def fused(self, Tk: int, Tu: int) -> bool:
-        """True when the single-kernel similarity+stem path covers this model (kws_sim_stem_supported)."""
-        return self.w.stem_wf is not None and ops.sim_stem_supported(self.w.C, Tk, Tu, self.w.Dk)
+    def fused(self, Tk: int, Tu: int, out_mode: int = ops.STEM_OUT_NHWC_BF16) -> bool:
+        """True when the fused similarity+stem kernel covers this model and output mode
+        (kws_sim_stem_supported; more than 12 layers run as channel-group passes, bf16 output only)."""
+        return self.w.stem_wf is not None and ops.sim_stem_supported(self.w.C, Tk, Tu, self.w.Dk, out_mode)
 
     def hot_path(self, kwd_n: torch.Tensor, utt_n: torch.Tensor, out_mode: int, max_pairs: int = 1024,
                  consume: Optional[Callable] = None, bufs: Optional[dict] = None,
@@ -156,7 +157,7 @@ class KWSEngine:
         Cc, K, Tk, Dk = kwd_n.shape
         _, U, Tu, _ = utt_n.shape
         bufs = bufs if bufs is not None else {}
-        fused = self.fused(Tk, Tu)
+        fused = self.fused(Tk, Tu, out_mode)
         Ho, Wo = (Tk + 1) // 2, (Tu + 1) // 2
         f32 = out_mode == ops.STEM_OUT_NCHW_F32
         n = 0

@@ -179,7 +179,7 @@ class B200ForwardMixin:
             lowp = self.b200_body_dtype != "float32"
             out_mode = ops.STEM_OUT_NHWC_BF16 if lowp else ops.STEM_OUT_NCHW_F32
             f32 = None
-            if not self.b200_return_features and eng.fused(Tk_s, Tu_s):
+            if not self.b200_return_features and eng.fused(Tk_s, Tu_s, out_mode):
                 # KWSOutput.features is read by no caller of the reference; without it the
                 # similarity tensor never reaches HBM
                 st = ops.sim_stem(kwd_n, utt_n, eng.w.stem_wf, eng.w.stem_b, out_mode, diag=diag)

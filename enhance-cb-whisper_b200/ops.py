@@ -237,8 +237,10 @@ def stem(feat_f16: torch.Tensor, Tu: int, w_packed: torch.Tensor, bias: torch.Te
     return out
 
 
-def sim_stem_supported(Cc: int, Tk: int, Tu: int, Dk: int) -> bool:
-    return bool(_lib.load().kws_sim_stem_supported(Cc, Tk, Tu, Dk))
+def sim_stem_supported(Cc: int, Tk: int, Tu: int, Dk: int, out_mode: int = STEM_OUT_NHWC_BF16) -> bool:
+    """kws_sim_stem_supported: 1 = both output modes, 2 = bf16 channels-last only (C > 12, multi-pass), 0 = no."""
+    r = _lib.load().kws_sim_stem_supported(Cc, Tk, Tu, Dk)
+    return r == 1 or (r == 2 and out_mode == STEM_OUT_NHWC_BF16)
 
 
 def sim_stem(kwd_n: torch.Tensor, utt_n: torch.Tensor, w_fused: torch.Tensor, bias: torch.Tensor, out_mode: int,
@@ -268,7 +270,7 @@ def sim_stem(kwd_n: torch.Tensor, utt_n: torch.Tensor, w_fused: torch.Tensor, bi
     check(lib.kws_sim_stem_range(_cuda(kwd_n, "kwd_n", torch.float16), _cuda(utt_n, "utt_n", torch.float16), Cc, K,
                                  U, Tk, Tu, Dk, PAIRS_DIAG if diag else PAIRS_ALL, k0, k1 - k0, u0, u1 - u0,
                                  _cuda(w_fused, "w_fused", torch.float16), _cuda(bias, "bias", torch.float32),
-                                 out_mode, _cuda(out, "out"), _stream()), "kws_sim_stem")
+                                 out_mode, _cuda(out, "out"), _stream()), "kws_sim_stem", launches=(Cc + 11) // 12)
     shape = (pairs, 64, Ho, Wo) if f32 else (pairs, Ho, Wo, 64)
     view = out.view(-1)[: pairs * 64 * Ho * Wo].view(shape)
     if out_mode == STEM_OUT_NHWC_BF16:

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define KWS_ABI_VERSION 4
+#define KWS_ABI_VERSION 5
 
 /* 16-bit operand formats (same encoding as the tcgen05 kind::f16 descriptor) */
 #define KWS_F16 0  /* IEEE half: 10-bit mantissa; for L2-normalised data and sane weights */
@@ -156,7 +156,9 @@ size_t kws_stem_workspace_bytes(int pairs, int C, int Tk, int Tu);
  * (replaces model.py:174-191,:217 and HF modeling_resnet.py:39-54 via resnet.py:38,53 together).
  *   kwd_n fp16 [C,K,Tk,Dk], utt_n fp16 [C,U,Tu,Dk] (prepared operands, mask folded)
  *   w_fused/bias from kws_pack_stem_fused; pair_mode / out_mode / out as kws_sim / kws_stem
- *   Requires C <= 12 and Dk % 64 == 0 (kws_sim_stem_supported() != 0); other shapes use
+ *   Requires Dk % 64 == 0.  C <= 12 runs as one launch in either output mode
+ *   (kws_sim_stem_supported() == 1); 12 < C <= 64 runs one launch per group of 12 layers, the passes chaining
+ *   fp16 partial sums through `out` itself, bf16 channels-last output only (== 2); otherwise (== 0) use
  *   kws_sim + kws_stem.                                                                     */
 int kws_sim_stem(const void* kwd_n, const void* utt_n, int C, int K, int U, int Tk, int Tu, int Dk, int pair_mode,
                  const void* w_fused, const float* bias, int out_mode, void* out, void* stream);
