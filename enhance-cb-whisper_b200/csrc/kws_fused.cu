@@ -211,7 +211,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
     for (int i = threadIdx.x; i < w16; i += G_THREADS) reinterpret_cast<uint4*>(s_w)[i] = p.w[i];
     // the ring is zeroed once: chunks nobody writes (Y' of the last pixel, unused planes for C <= 8) must hold
     // finite values, they only ever meet zero weights or discarded pixel slots
-    for (int i = threadIdx.x; i < G_RING_BYTES / 16; i += G_THREADS)
+    for (int i = threadIdx.x; i < (G_RING_BYTES - 64) / 16; i += G_THREADS)  // the last block's pad holds the barriers
       reinterpret_cast<uint4*>(s_ring)[i] = make_uint4(0u, 0u, 0u, 0u);
     if (threadIdx.x < G_OC) s_bias[threadIdx.x] = __ldg(p.bias + threadIdx.x);
     if ((smem_u32(smem_raw) & 1023u) != 0) {
