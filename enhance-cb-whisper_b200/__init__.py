@@ -9,6 +9,6 @@ root maps one onto the other).
 from ._lib import KWSError, LIB_PATH  # noqa: F401
 from .model import KWSModelB200, KWSOutput, Resnet  # noqa: F401
 from .engine import KWSEngine, PackedWeights, pack_weights  # noqa: F401
-from . import cbw  # noqa: F401
+from . import bank, cbw  # noqa: F401
 
-__all__ = ["KWSModelB200", "KWSOutput", "Resnet", "KWSEngine", "PackedWeights", "pack_weights", "KWSError", "cbw"]
+__all__ = ["KWSModelB200", "KWSOutput", "Resnet", "KWSEngine", "PackedWeights", "pack_weights", "KWSError", "bank", "cbw"]
