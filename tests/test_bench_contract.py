@@ -1,0 +1,43 @@
+"""bench.py contract pieces that can be checked without a GPU: workload table vs BASELINE.md section 5,
+argument defaults, the JSON keys of the reference arm (run on a tiny budget)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_work_per_pair_matches_baseline_md():
+    sys.path.insert(0, ROOT)
+    import bench
+
+    # GFLOP per pair (similarity + stem)
+    for name, sim, stem in (("cfg1", 0.691, 1.411), ("cfg2", 0.346, 4.234), ("cfg3", 0.230, 2.860)):
+        s, t = bench.flops_per_pair(bench.WORKLOADS[name])
+        assert abs(s / 1e9 - sim) < 2e-3 and abs(t / 1e9 - stem) < 2e-3, (name, s, t)
+    wl = bench.WORKLOADS["cfg2"]
+    assert (wl["K"], wl["U"], wl["C"], wl["D"], wl["P"], wl["Tk"], wl["Tu"]) == (1000, 256, 12, 768, 64, 150, 1500)
+    # projection: SURVEY 8d, 4.09 TFLOP in total at cfg2
+    assert abs(bench.flops_projection(wl, wl["K"], wl["U"]) / 1e12 - 4.09) < 0.05
+
+
+def test_b200_arm_refuses_to_run_without_cuda():
+    import torch
+
+    if torch.cuda.is_available():
+        return
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_reference_arm_prints_the_contract_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "cfg1",
+                        "--steps", "1", "--warmup", "1", "--ref-budget", "6"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "kwd_utt_pairs_per_s" and line["unit"] == "pairs/s"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
