@@ -86,8 +86,11 @@ constexpr int G_MAX_MMA = 3;                       // stem MMAs per kernel row
 constexpr int G_W_BYTES = 7 * G_MAX_MMA * G_MMA_W_BYTES;  // 86016
 constexpr int G_NS = 3;                            // similarity operand stages
 constexpr int G_A_BYTES = 128 * 128;               // utt tile 128 px x 64 dims (SW128)
-constexpr int G_B_BYTES = 16 * 128;                // kwd tile 16 rows x 64 dims (SW128)
-constexpr int G_STAGE = G_A_BYTES + G_B_BYTES;     // 18432
+// Similarity chunk = ROWS keyword frames per MMA (N = ROWS): 16 for up to 12 layers, 32 for <= 6, 48 for <= 4
+// (the TMEM region holds C x ROWS <= 192 columns, the converters C/2 x ROWS <= 96 packed registers).  Wide
+// models with few layers (the L variant: Dk = 384..1280) spend most of their time in the similarity GEMM;
+// a larger N reads the utterance tile once per 48 instead of 16 frames.
+__host__ __device__ constexpr int g_stage_bytes(int rows) { return G_A_BYTES + rows * 128; }
 constexpr int G_MAX_C = 12;
 constexpr int G_ACC_COLS = 128;                    // one stem accumulator: half a | half b
 constexpr int G_TMEM_SIM = 2 * G_ACC_COLS;         // similarity region starts at column 256
@@ -108,7 +111,8 @@ struct FusedParams {
   int n_mma;     // stem MMAs per kernel row: 2 (C <= 8) or 3
   int nP;        // stem steps per item = ceil(Ho / 2)
   int nQ;        // quanta (4 input rows) converted per item = nP + 2
-  int n_chunks;  // similarity chunks (16 input rows) per item = ceil(nQ / 4)
+  int n_chunks;  // similarity chunks (ROWS input rows = ROWS/4 quanta) per item
+  int w_bytes;   // bytes of this pass's stem weights in shared memory (7 * n_mma * 4096)
   int diag;
   long long num_items;
   long long* dbg;  // optional [grid][16] cycle counters (issuer 0-4, epilogue 5-7, converter 8-11; development aid), or null
@@ -179,16 +183,20 @@ __device__ __forceinline__ ItemCoord decode_item(const FusedParams& p, long long
   return r;
 }
 
-template <bool NHWC>  // NHWC: bf16 channels-last through TMA stores; else fp32 NCHW with direct stores (parity)
+// NHWC: bf16 channels-last through TMA stores; else fp32 NCHW with direct stores (parity).  ROWS: see above.
+template <bool NHWC, int ROWS>
 __global__ void __launch_bounds__(G_THREADS, 1)
 kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_constant__ CUtensorMap map_kwd,
                  const __grid_constant__ CUtensorMap map_out_lo, const __grid_constant__ CUtensorMap map_out_hi,
                  const FusedParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = smem_raw;  // no alignment slack to spare: the declared 1024-byte alignment is checked below
+  constexpr int G_STAGE = g_stage_bytes(ROWS);
+  constexpr int NPAIR = 96 / ROWS;                // layer pairs the converters can hold: 6 / 3 / 2
+  constexpr int QPC = ROWS / 4;                   // quanta per similarity chunk
   uint8_t* s_ops = base;                          // G_NS * G_STAGE (each 1024-aligned)
-  uint8_t* s_w = s_ops + G_NS * G_STAGE;          // G_W_BYTES
-  uint8_t* s_ostage = s_w + G_W_BYTES;            // G_OUT_STAGE (4 x 4 KB, each 1024-aligned)
+  uint8_t* s_w = s_ops + G_NS * G_STAGE;          // p.w_bytes (multiple of 4096)
+  uint8_t* s_ostage = s_w + p.w_bytes;            // G_OUT_STAGE (4 x 4 KB, each 1024-aligned)
   uint8_t* s_ring = s_ostage + G_OUT_STAGE;       // G_RING_BYTES
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + G_RING_BYTES - 64);  // from the last block's (unused) bank pad on
   uint64_t* ofull = bars;                 // [G_NS] TMA -> MMA (similarity operands)
@@ -276,7 +284,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
               uint8_t* sa = s_ops + stage * G_STAGE;
               mbar_arrive_expect_tx(&ofull[stage], G_STAGE);
               tma_load_3d(&map_utt, &ofull[stage], sa, kb * 64, jbase, (p.c0 + c) * p.U + w.u);
-              tma_load_3d(&map_kwd, &ofull[stage], sa + G_A_BYTES, kb * 64, 16 * n - 3, (p.c0 + c) * p.K + w.kw);
+              tma_load_3d(&map_kwd, &ofull[stage], sa + G_A_BYTES, kb * 64, ROWS * n - 3, (p.c0 + c) * p.K + w.kw);
               if (++stage == G_NS) stage = 0, phase ^= 1;
             }
           }
@@ -288,7 +296,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
     // Runs as far ahead as the operand stages and the single TMEM region allow; its barrier polls never
     // hold up the stem issuer (warp 1), and its MMAs fill the tensor pipe while that one polls.
     if (elect_one()) {
-      const uint32_t idesc_sim = make_idesc_f16(128, 16, 0);
+      const uint32_t idesc_sim = make_idesc_f16(128, ROWS, 0);
       const uint32_t ops_u32 = smem_u32(s_ops);
       const uint64_t sdesc0 = make_smem_desc(0, 16, 1024, LAYOUT_SW128);
       int o_stage = 0;
@@ -304,7 +312,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
             mbar_wait(&ofull[o_stage], o_phase, 300 + o_stage);
             if (st == 0) KWS_TRACE(2, g, 4);
             tc_fence_after();
-            const uint32_t d = G_TMEM_SIM + c * 16;  // TMEM base is 0 (checked at start)
+            const uint32_t d = G_TMEM_SIM + c * ROWS;  // TMEM base is 0 (checked at start)
             const uint32_t sa = ops_u32 + o_stage * G_STAGE;
             const uint64_t adesc = sdesc0 + (uint64_t)(sa >> 4);
             const uint64_t bdesc = adesc + (uint64_t)(G_A_BYTES >> 4);
@@ -603,42 +611,47 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
     uint32_t Gq = 0;  // global quantum counter
     long long tc_sfull = 0, tc_qempty = 0, tc_ld = 0, tc_st = 0;
     for (long long it = blockIdx.x; it < p.num_items; it += gridDim.x) {
-      for (int q0 = 0; q0 < p.nQ; q0 += 4, ++g) {
-        const int nq = p.nQ - q0 < 4 ? p.nQ - q0 : 4;
+      for (int q0 = 0; q0 < p.nQ; q0 += QPC, ++g) {
+        const int nq = p.nQ - q0 < QPC ? p.nQ - q0 : QPC;
         const long long c0 = KWS_CLK();
         const long long c1 = c0;
         if (warp == 8 && lane == 0) KWS_TRACE(2, g, 0);
-        // pull the chunk layer pair by layer pair (16 rows x 2 layers per TMEM round trip); each pair's tiles go
+        // pull the chunk layer pair by layer pair (ROWS rows x 2 layers per TMEM round trip); each pair's tiles go
         // back to the similarity issuer at once, so the next chunk is computed while this one is still being pulled
-        uint32_t h2[16][G_NPAIR];  // [row][layer pair] fp16x2
+        uint32_t h2[ROWS][NPAIR];  // [row][layer pair] fp16x2
 #pragma unroll
-        for (int j = 0; j < G_NPAIR; ++j) {
+        for (int j = 0; j < NPAIR; ++j) {
           if (2 * j < p.C) {
             mbar_wait(&sfull[j], g & 1, 700 + j);
             tc_fence_after();
-            uint32_t v0[16], v1[16];
-            tmem_ld16(t_lane + (2 * j) * 16, v0);
-            if (2 * j + 1 < p.C) {
-              tmem_ld16(t_lane + (2 * j + 1) * 16, v1);
-            } else {
 #pragma unroll
-              for (int r = 0; r < 16; ++r) v1[r] = 0u;
+            for (int b = 0; b < ROWS / 16; ++b) {  // 16 rows x 2 layers per TMEM round trip (32 transient registers)
+              uint32_t v0[16], v1[16];
+              tmem_ld16(t_lane + (2 * j) * ROWS + 16 * b, v0);
+              if (2 * j + 1 < p.C) {
+                tmem_ld16(t_lane + (2 * j + 1) * ROWS + 16 * b, v1);
+              } else {
+#pragma unroll
+                for (int r = 0; r < 16; ++r) v1[r] = 0u;
+              }
+              tmem_ld_wait();
+              if (b == ROWS / 16 - 1) {
+                tc_fence_before();
+                mbar_arrive(&sempty[j]);
+              }
+#pragma unroll
+              for (int r = 0; r < 16; ++r) h2[16 * b + r][j] = pack_half2(__uint_as_float(v0[r]), __uint_as_float(v1[r]));
             }
-            tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive(&sempty[j]);
-#pragma unroll
-            for (int r = 0; r < 16; ++r) h2[r][j] = pack_half2(__uint_as_float(v0[r]), __uint_as_float(v1[r]));
           } else {
 #pragma unroll
-            for (int r = 0; r < 16; ++r) h2[r][j] = 0u;
+            for (int r = 0; r < ROWS; ++r) h2[r][j] = 0u;
           }
         }
         const long long c2 = KWS_CLK();
         if (warp == 8 && lane == 0) KWS_TRACE(2, g, 1);
         tc_sfull += c1 - c0, tc_ld += c2 - c1;
 #pragma unroll
-        for (int qq = 0; qq < 4; ++qq) {
+        for (int qq = 0; qq < QPC; ++qq) {
           if (qq < nq) {
             const long long c3 = KWS_CLK();
             mbar_wait(&qempty[Gq & 3], ((Gq >> 2) & 1) ^ 1, 800 + (int)(Gq & 3));
@@ -649,11 +662,13 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
               // input row r = 4q + t - 3: parity (t+1)&1, ring slot (2 Gq + (t >> 1)) mod NR
               const uint32_t slot = (2 * Gq + (t >> 1)) & (G_NR - 1);
               uint8_t* d0 = dst_px + ((t + 1) & 1) * 2 * G_BLOCK + slot * 1024;
-              const uint4 vx = make_uint4(h2[4 * qq + t][0], h2[4 * qq + t][1], h2[4 * qq + t][2], h2[4 * qq + t][3]);
+              const uint4 vx = make_uint4(h2[4 * qq + t][0], NPAIR > 1 ? h2[4 * qq + t][NPAIR > 1 ? 1 : 0] : 0u,
+                                          NPAIR > 2 ? h2[4 * qq + t][NPAIR > 2 ? 2 : 0] : 0u,
+                                          NPAIR > 3 ? h2[4 * qq + t][NPAIR > 3 ? 3 : 0] : 0u);
               *reinterpret_cast<uint4*>(d0) = vx;
               if (slot == 0) *reinterpret_cast<uint4*>(d0 + G_NR * 1024) = vx;  // mirror: tap windows never wrap
-              if (yp) {
-                const uint2 vy = make_uint2(h2[4 * qq + t][4], h2[4 * qq + t][5]);
+              if (NPAIR > 5 && yp) {
+                const uint2 vy = make_uint2(h2[4 * qq + t][NPAIR > 5 ? 4 : 0], h2[4 * qq + t][NPAIR > 5 ? 5 : 0]);
                 uint8_t* dy = d0 + 4 * G_BLOCK;
                 *reinterpret_cast<uint2*>(dy) = vy;                    // own chunk, elements 0..3
                 if (has_left) *reinterpret_cast<uint2*>(dy - 8) = vy;  // left neighbour's chunk, elements 4..7
@@ -686,8 +701,12 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
   }
 }
 
-constexpr size_t G_SMEM = (size_t)G_NS * G_STAGE + G_W_BYTES + G_OUT_STAGE + G_RING_BYTES - 64 + G_NBAR * 8 + 16 + G_OC * 4;
-static_assert(G_SMEM <= 232448, "fused kernel exceeds the 227 KB shared-memory limit");
+constexpr size_t g_smem_bytes(int rows, int n_mma) {
+  return (size_t)G_NS * g_stage_bytes(rows) + (size_t)7 * n_mma * G_MMA_W_BYTES + G_OUT_STAGE + G_RING_BYTES - 64 +
+         G_NBAR * 8 + 16 + G_OC * 4;
+}
+static_assert(g_smem_bytes(16, 3) <= 232448 && g_smem_bytes(32, 2) <= 232448 && g_smem_bytes(48, 2) <= 232448,
+              "fused kernel exceeds the 227 KB shared-memory limit");
 
 // Fused-kernel weight layout: [di 7][m n_mma][chunk 2][n 128][e 8] fp16, BN scale folded.
 //   n < 64: half a (output channel n); n >= 64: half b (output channel n - 64, tap dj + 4)
@@ -727,6 +746,9 @@ using namespace kws;
 
 static long long* g_fused_dbg = nullptr;
 static int g_fused_grid_limit = 0;
+static int g_fused_rows = 0;
+// development aid: force the similarity chunk height (16 | 32 | 48) instead of choosing it from the layer count
+extern "C" void kws_debug_set_fused_rows(int rows) { g_fused_rows = rows; }
 // development aid: cap the number of CTAs (to separate per-SM limits from chip-wide L2 limits)
 extern "C" void kws_debug_set_fused_grid_limit(int n) { g_fused_grid_limit = n; }
 
@@ -794,20 +816,12 @@ extern "C" int kws_sim_stem_range(const void* kwd_n, const void* utt_n, int C, i
                 out_mode);
   KWS_CHECK_ARG((reinterpret_cast<uintptr_t>(w_fused) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                 "sim_stem: pointers must be 16-byte aligned");
-  CUtensorMap mu, mk;
+  CUtensorMap mu;
   {
     const uint64_t dims[3] = {(uint64_t)Dk, (uint64_t)Tu, (uint64_t)C * U};
     const uint64_t strides[2] = {(uint64_t)Dk * 2, (uint64_t)Dk * 2 * (uint64_t)Tu};
     const uint32_t box[3] = {64, 128, 1};
     if (int e = make_tensor_map(&mu, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, utt_n, dims, strides, box,
-                                CU_TENSOR_MAP_SWIZZLE_128B))
-      return e;
-  }
-  {
-    const uint64_t dims[3] = {(uint64_t)Dk, (uint64_t)Tk, (uint64_t)C * K};
-    const uint64_t strides[2] = {(uint64_t)Dk * 2, (uint64_t)Dk * 2 * (uint64_t)Tk};
-    const uint32_t box[3] = {64, 16, 1};
-    if (int e = make_tensor_map(&mk, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, kwd_n, dims, strides, box,
                                 CU_TENSOR_MAP_SWIZZLE_128B))
       return e;
   }
@@ -840,11 +854,9 @@ extern "C" int kws_sim_stem_range(const void* kwd_n, const void* utt_n, int C, i
   p.col_tiles = (p.Wo + G_TILE_OJ - 1) / G_TILE_OJ;
   p.nP = (p.Ho + 1) / 2;
   p.nQ = p.nP + 2;
-  p.n_chunks = (p.nQ + 3) / 4;
+
   p.diag = pair_mode == KWS_PAIRS_DIAG;
   p.num_items = (long long)nk * (p.diag ? 1 : nu) * p.col_tiles;
-  auto kern = out_mode == KWS_STEM_OUT_NHWC_BF16 ? kws_fused_kernel<true> : kws_fused_kernel<false>;
-  KWS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM));
   long long grid = p.num_items;
   const int sms = sm_count();
   if (grid > sms) grid = sms;
@@ -859,7 +871,27 @@ extern "C" int kws_sim_stem_range(const void* kwd_n, const void* utt_n, int C, i
     p.c0 = g * G_MAX_C;
     p.n_mma = fused_n_mma(Cg);
     p.acc_mode = n_groups == 1 ? 0 : (g == 0 ? 1 : (g == n_groups - 1 ? 3 : 2));
-    kern<<<(int)grid, G_THREADS, G_SMEM, (cudaStream_t)stream>>>(mu, mk, mo_lo, mo_hi, p);
+    p.w_bytes = (int)fused_group_bytes(Cg);
+    const int rows = g_fused_rows > 0 ? g_fused_rows : (Cg <= 4 ? 48 : (Cg <= 6 ? 32 : 16));
+    KWS_CHECK_ARG(rows == 16 || (rows == 32 && Cg <= 6) || (rows == 48 && Cg <= 4), "sim_stem: bad chunk rows %d", rows);
+    p.n_chunks = (p.nQ + rows / 4 - 1) / (rows / 4);
+    CUtensorMap mk;
+    {
+      const uint64_t dims[3] = {(uint64_t)Dk, (uint64_t)Tk, (uint64_t)C * K};
+      const uint64_t strides[2] = {(uint64_t)Dk * 2, (uint64_t)Dk * 2 * (uint64_t)Tk};
+      const uint32_t box[3] = {64, (uint32_t)rows, 1};
+      if (int e = make_tensor_map(&mk, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, kwd_n, dims, strides, box,
+                                  CU_TENSOR_MAP_SWIZZLE_128B))
+        return e;
+    }
+    const bool nh = out_mode == KWS_STEM_OUT_NHWC_BF16;
+    void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, FusedParams) =
+        rows == 48 ? (nh ? kws_fused_kernel<true, 48> : kws_fused_kernel<false, 48>)
+        : rows == 32 ? (nh ? kws_fused_kernel<true, 32> : kws_fused_kernel<false, 32>)
+                     : (nh ? kws_fused_kernel<true, 16> : kws_fused_kernel<false, 16>);
+    const size_t smem = g_smem_bytes(rows, p.n_mma);
+    KWS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(int)grid, G_THREADS, smem, (cudaStream_t)stream>>>(mu, mk, mo_lo, mo_hi, p);
     KWS_CUDA(cudaGetLastError());
     wsrc += fused_group_bytes(Cg);
   }
