@@ -1,0 +1,170 @@
+"""GPU: the drop-in module (KWSModelB200.forward / .score, through the C ABI) against the committed golden
+fixtures, i.e. against what the UNMODIFIED reference ``KWSModel.forward`` returned for the same seeded inputs
+and weights (oracle/make_golden.py).  Tolerances are the north-star's: similarity and logits within 2e-3
+absolute (fp32 accumulation, fp32 body, TF32 off), thresholded detections identical."""
+import pytest
+import torch
+
+from oracle import kws_oracle as O
+from oracle.make_golden import CASES, assemble_body, load_case
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-3
+
+
+def build(name, dev, **opts):
+    import enhance_cb_whisper_b200 as kb
+
+    meta, ins, sd, outs = load_case(name)
+    fe, head, same = assemble_body(meta, sd)
+    v = meta["variant"]
+    m = kb.KWSModelB200(n_layers=meta["C"], embedding_dim=meta["D"], proj_mlp_units=meta["P"],
+                        learn_features=(v != "L"), proj_mlp=(v != "L"), frames_conv=(v == "LEF"),
+                        resnet_version=meta["resnet_version"], features_size=(meta["Tk"], meta["Tu"]), **opts)
+    full = dict(m.state_dict())
+    full.update({"model.feature_extractor." + k: t for k, t in fe.state_dict().items()})
+    full.update({"model.classifier." + k: t for k, t in head.state_dict().items()})
+    full.update(sd)
+    m.load_state_dict(full)
+    m = m.to(dev).eval()
+    km, um = ins["kwd_mask"], ins["utt_mask"]
+    if v == "LEF":  # the reference forward needs masks at pooled resolution (SURVEY 8c deviation ii)
+        km, um = O.pooled_mask(km), O.pooled_mask(um)
+    dev_ins = dict(kwd=ins["kwd"].to(dev), utt=ins["utt"].to(dev), km=km.contiguous().to(dev),
+                   um=um.contiguous().to(dev), hot=ins["hotword_mask"].to(dev))
+    return m, meta, dev_ins, outs, same
+
+
+def err(a, b):
+    return (a.float().cpu() - b.float().cpu()).abs().max().item()
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_forward_matches_reference_outputs(built_lib, cuda_dev, name):
+    """forward() driven like test_step (model.py:756-780): one utterance at a time, batch dim 1."""
+    m, meta, x, outs, same = build(name, cuda_dev)
+    assert same, "regenerated ResNet body differs from the one the fixture was made with"
+    for u in range(meta["U"]):
+        r = m(kwd_features=x["kwd"], utt_features=x["utt"][u:u + 1], kwd_mask=x["km"], utt_mask=x["um"][u:u + 1])
+        assert r.features.shape == outs["features"][:, u].shape and r.logits.shape == (meta["K"], 2)
+        assert err(r.features, outs["features"][:, u]) <= TOL
+        assert err(r.logits, outs["logits"][:, u]) <= TOL
+        assert r.loss is None and r.logits_alt is None and r.loss_alt == {"loss_diag": None, "loss_resnet": None}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_fused_forward_skips_the_similarity_tensor(built_lib, cuda_dev, name):
+    """b200_return_features=False: similarity + stem in one kernel, KWSOutput.features is None (no reference
+    caller reads it), logits unchanged."""
+    m, meta, x, outs, _ = build(name, cuda_dev, b200_return_features=False)
+    labels = torch.zeros(meta["K"], dtype=torch.long, device=cuda_dev)
+    for u in range(meta["U"]):
+        r = m(kwd_features=x["kwd"], utt_features=x["utt"][u:u + 1], labels=labels, kwd_mask=x["km"],
+              utt_mask=x["um"][u:u + 1])
+        assert r.features is None
+        assert err(r.logits, outs["logits"][:, u]) <= TOL
+        exp_loss = torch.nn.functional.cross_entropy(outs["logits"][:, u], labels.cpu())
+        assert abs(r.loss.item() - exp_loss.item()) <= TOL
+        assert r.loss_alt["loss_resnet"] is r.loss
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_stem_activation_matches_reference_hook(built_lib, cuda_dev, name):
+    """The in-scope end point: stem activation of every pair vs the reference's embedder output."""
+    from enhance_cb_whisper_b200 import ops
+
+    m, meta, x, outs, _ = build(name, cuda_dev)
+    eng = m.prepare(cuda_dev)
+    kn = eng.compress(x["kwd"], x["km"])
+    un = eng.compress(x["utt"], x["um"])
+    got = {}
+    eng.hot_path(kn, un, ops.STEM_OUT_NCHW_F32, max_pairs=4,
+                 consume=lambda k0, k1, u0, u1, st: got.__setitem__((k0, k1, u0, u1), st.clone()))
+    exp = outs["stem"]  # [K,U,64,Ho,Wo]
+    for (k0, k1, u0, u1), st in got.items():
+        e = exp[k0:k1, u0:u1].flatten(0, 1)
+        assert st.shape == e.shape
+        assert err(st, e) <= TOL * max(1.0, e.abs().max().item())
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_score_detections_identical(built_lib, cuda_dev, name):
+    """score(): all K x U pairs in one call == the reference's per-group loop; detections bit-identical."""
+    m, meta, x, outs, _ = build(name, cuda_dev)
+    gold = outs["scores"]  # softmax(logits)[:,1] * hotword_mask (model.py:783-795)
+    # a threshold in the widest gap of the golden scores: every pair has a margin, so detections must be identical
+    s = torch.sort(gold.flatten()).values
+    gaps = s[1:] - s[:-1]
+    i = int(torch.argmax(gaps))
+    thr = float((s[i] + s[i + 1]) / 2)
+    sc, det, logits = m.score(x["kwd"], x["utt"], x["km"], x["um"], hotword_mask=x["hot"], max_pairs=5, threshold=thr)
+    assert err(logits, outs["logits"]) <= TOL
+    assert err(sc, gold) <= TOL
+    if float(gaps[i]) > 2.5 * TOL:  # margin gap/2 > |score error| (<= |logit error| / 2): nothing may flip
+        assert torch.equal(det.cpu().bool(), gold >= thr)
+    sure = (gold - thr).abs() > TOL
+    assert torch.equal(det.cpu().bool()[sure], (gold >= thr)[sure])
+    # default threshold (hparams.threshold = 0.5): identical wherever the reference score has a margin
+    _, det05, _ = m.score(x["kwd"], x["utt"], x["km"], x["um"], hotword_mask=x["hot"])
+    clear = (gold - 0.5).abs() > TOL
+    assert torch.equal(det05.cpu().bool()[clear], (gold >= 0.5)[clear])
+    ghosts = x["hot"].cpu() == 0
+    if ghosts.any():
+        assert float(sc.cpu()[ghosts].abs().max()) == 0.0
+
+
+def test_training_style_batch_is_diagonal(built_lib, cuda_dev):
+    """utt batch == keyword batch: pair k with utterance k (model.py:171-173; training_step batches)."""
+    m, meta, x, outs, _ = build("LE_small", cuda_dev)
+    K, U = meta["K"], meta["U"]
+    idx = [k % U for k in range(K)]
+    utt = x["utt"][idx].contiguous()
+    um = x["um"][idx].contiguous()
+    r = m(kwd_features=x["kwd"], utt_features=utt, kwd_mask=x["km"], utt_mask=um)
+    for k in range(K):
+        assert err(r.features[k], outs["features"][k, idx[k]]) <= TOL
+        assert err(r.logits[k], outs["logits"][k, idx[k]]) <= TOL
+
+
+def test_interface_errors_mirror_the_reference(built_lib, cuda_dev):
+    m, meta, x, _, _ = build("L_small", cuda_dev)
+    with pytest.raises(AttributeError):  # reference: None.unsqueeze (model.py:187-191)
+        m(kwd_features=x["kwd"], utt_features=x["utt"][:1])
+    with pytest.raises(ValueError):  # HF channel check (modeling_resnet.py:71-75)
+        m(kwd_features=x["kwd"][:, :2], utt_features=x["utt"][:1, :2], kwd_mask=x["km"][:, :2], utt_mask=x["um"][:1, :2])
+    m.train()
+    with pytest.raises(RuntimeError):  # inference only: BatchNorm is folded
+        m(kwd_features=x["kwd"], utt_features=x["utt"][:1], kwd_mask=x["km"], utt_mask=x["um"][:1])
+    m.eval()
+    from enhance_cb_whisper_b200 import KWSError
+
+    with pytest.raises(KWSError):  # no CPU fallback
+        m.prepare(torch.device("cpu"))
+
+
+def test_lef_many_layers_runs_fused_in_passes(built_lib, cuda_dev):
+    """LEF with 16 layers (cfg3/cfg5 style): the throughput path runs the fused kernel in passes over groups of
+    12 layers; its bf16 stem activation matches the oracle's fp32 stem."""
+    import enhance_cb_whisper_b200 as kb
+    from enhance_cb_whisper_b200 import ops
+
+    C, D, P, Tk, Tu, K, U = 16, 128, 64, 22, 70, 3, 2
+    torch.manual_seed(2)
+    m = kb.KWSModelB200(n_layers=C, embedding_dim=D, proj_mlp_units=P, learn_features=True, proj_mlp=True,
+                        frames_conv=True, resnet_version="resnet-18", features_size=(Tk, Tu))
+    sd = O.make_weights("LEF", C, D, P, seed=77)
+    full = dict(m.state_dict())
+    full.update(sd)
+    m.load_state_dict(full)
+    m = m.to(cuda_dev).eval()
+    kwd, utt, km, um, _ = O.make_inputs(K, U, C, D, Tk, Tu, seed=78, ghost_frac=0.0)
+    km, um = O.pooled_mask(km).contiguous(), O.pooled_mask(um).contiguous()
+    exp = O.forward_pairs(kwd, utt, km, um, sd, "LEF", upto="stem")["stem"].flatten(0, 1)
+    eng = m.prepare(cuda_dev)
+    kn = eng.compress(kwd.to(cuda_dev), km.to(cuda_dev))
+    un = eng.compress(utt.to(cuda_dev), um.to(cuda_dev))
+    assert eng.fused(kn.shape[2], un.shape[2], ops.STEM_OUT_NHWC_BF16)
+    got = []
+    eng.hot_path(kn, un, ops.STEM_OUT_NHWC_BF16, max_pairs=K * U, consume=lambda *a: got.append(a[-1].float().clone()))
+    assert got[0].shape == exp.shape
+    assert err(got[0], exp) <= 2e-2 * max(1.0, exp.abs().max().item() / 4)
