@@ -50,9 +50,11 @@ WORKLOADS = {
     "cfg2": dict(variant="LE", C=12, stack=12, D=768, P=64, Tk=150, Tu=1500, K=1000, U=256,
                  desc="cfg2 LE: whisper-small shape, 12 layers x 768-d -> P=64, 150x1500 frames, "
                       "1000 kw x 256 utt per GPU"),
-    "cfg3": dict(variant="LEF", C=32, stack=32, D=1280, P=64, Tk=150, Tu=1500, K=10000, U=256,
+    # the raw fp32 bank of all 10 000 keywords is 245 GB: production streams it through the compression kernels
+    # (bank.build_keyword_bank); the bench keeps a 2000 x 128 slab of the job resident (49 GB + 31 GB)
+    "cfg3": dict(variant="LEF", C=32, stack=32, D=1280, P=64, Tk=150, Tu=1500, K=2000, U=128,
                  desc="cfg3 LEF: whisper-large-v3 shape, 32 layers x 1280-d -> P=64, 75x750 frames, "
-                      "10000 kw x 256 utt"),
+                      "2000 kw x 128 utt slab of the 10000 x 256 job"),
 }
 METRIC = "kwd_utt_pairs_per_s"
 UNIT = "pairs/s"
