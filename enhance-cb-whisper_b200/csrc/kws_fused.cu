@@ -184,7 +184,8 @@ __device__ __forceinline__ ItemCoord decode_item(const FusedParams& p, long long
 }
 
 // NHWC: bf16 channels-last through TMA stores; else fp32 NCHW with direct stores (parity).  ROWS: see above.
-template <bool NHWC, int ROWS>
+// MULTI: channel-group passes (acc_mode 1..3) compiled in; single-pass launches use the leaner instance.
+template <bool NHWC, int ROWS, bool MULTI>
 __global__ void __launch_bounds__(G_THREADS, 1)
 kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_constant__ CUtensorMap map_kwd,
                  const __grid_constant__ CUtensorMap map_out_lo, const __grid_constant__ CUtensorMap map_out_hi,
@@ -452,7 +453,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
           oc_stride = (long long)p.Ho * p.Wo;
         }
         uint8_t* srow = my_stage + lane * 128;
-#pragma unroll
+#pragma unroll 1  // a real loop: the role loops are instruction-cache bound, not ILP bound
         for (int grp = 0; grp < 2; ++grp) {  // 32 output channels per TMEM round trip
           uint32_t va[2][16], vb[2][16];
 #pragma unroll
@@ -464,7 +465,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
             // the previous step's TMA store must have read this warp's staging buffer before it is reused
             if (lane == 0) {
               asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-              if (nhwc && p.acc_mode >= 2 && tile_ok) {
+              if (nhwc && MULTI && p.acc_mode >= 2 && tile_ok) {
                 // partial sums of the previous channel-group pass: same tile, same staging layout
                 mbar_arrive_expect_tx(&pload[q], (lo_warp ? 32u : (uint32_t)(G_TILE_OJ - 32)) * 128u);
                 asm volatile(
@@ -516,8 +517,8 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
           for (int h = 0; h < 2; ++h) {
             const int ch = grp * 2 + h;
             if constexpr (nhwc) {
-              const bool with_bias = p.acc_mode == 0 || p.acc_mode == 3;  // single or last channel-group pass
-              const bool add_prev = p.acc_mode >= 2 && tile_ok;
+              const bool with_bias = !MULTI || p.acc_mode == 0 || p.acc_mode == 3;  // single or last channel-group pass
+              const bool add_prev = MULTI && p.acc_mode >= 2 && tile_ok;
               uint8_t* c0p = srow + (((2 * ch) ^ (lane & 7)) << 4);
               uint8_t* c1p = srow + (((2 * ch + 1) ^ (lane & 7)) << 4);
               uint32_t prev[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
@@ -573,7 +574,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
           tp[7] = f2;
         }
         if constexpr (nhwc) {
-          if (p.acc_mode >= 2 && tile_ok) ++pl_seq;
+          if (MULTI && p.acc_mode >= 2 && tile_ok) ++pl_seq;
           fence_proxy_async();
           __syncwarp();
           if (lane == 0 && tile_ok) {
@@ -872,7 +873,7 @@ extern "C" int kws_sim_stem_range(const void* kwd_n, const void* utt_n, int C, i
     p.n_mma = fused_n_mma(Cg);
     p.acc_mode = n_groups == 1 ? 0 : (g == 0 ? 1 : (g == n_groups - 1 ? 3 : 2));
     p.w_bytes = (int)fused_group_bytes(Cg);
-    const int rows = g_fused_rows > 0 ? g_fused_rows : (Cg <= 4 ? 48 : (Cg <= 6 ? 32 : 16));
+    const int rows = n_groups > 1 ? 16 : (g_fused_rows > 0 ? g_fused_rows : (Cg <= 4 ? 48 : (Cg <= 6 ? 32 : 16)));
     KWS_CHECK_ARG(rows == 16 || (rows == 32 && Cg <= 6) || (rows == 48 && Cg <= 4), "sim_stem: bad chunk rows %d", rows);
     p.n_chunks = (p.nQ + rows / 4 - 1) / (rows / 4);
     CUtensorMap mk;
@@ -885,10 +886,15 @@ extern "C" int kws_sim_stem_range(const void* kwd_n, const void* utt_n, int C, i
         return e;
     }
     const bool nh = out_mode == KWS_STEM_OUT_NHWC_BF16;
-    void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, FusedParams) =
-        rows == 48 ? (nh ? kws_fused_kernel<true, 48> : kws_fused_kernel<false, 48>)
-        : rows == 32 ? (nh ? kws_fused_kernel<true, 32> : kws_fused_kernel<false, 32>)
-                     : (nh ? kws_fused_kernel<true, 16> : kws_fused_kernel<false, 16>);
+    void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, FusedParams);
+    if (p.acc_mode != 0) {
+      kern = kws_fused_kernel<true, 16, true>;  // groups of 12 (or the last 1..12) layers: 16-row chunks, bf16
+      KWS_CHECK_ARG(rows == 16 && nh, "sim_stem: internal: multi-pass needs 16-row chunks and bf16 output");
+    } else {
+      kern = rows == 48 ? (nh ? kws_fused_kernel<true, 48, false> : kws_fused_kernel<false, 48, false>)
+             : rows == 32 ? (nh ? kws_fused_kernel<true, 32, false> : kws_fused_kernel<false, 32, false>)
+                          : (nh ? kws_fused_kernel<true, 16, false> : kws_fused_kernel<false, 16, false>);
+    }
     const size_t smem = g_smem_bytes(rows, p.n_mma);
     KWS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(int)grid, G_THREADS, smem, (cudaStream_t)stream>>>(mu, mk, mo_lo, mo_hi, p);
