@@ -45,6 +45,9 @@ def _stale(target: str, deps) -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ_DIR, exist_ok=True)
     flags = list(NVCC_FLAGS)
+    if os.environ.get("KWS_WAIT_HINT_NS"):  # development aid: tune the mbarrier suspend-time hint
+        flags.append("-DKWS_WAIT_HINT_NS=" + os.environ["KWS_WAIT_HINT_NS"])
+        force = True
     if os.environ.get("KWS_FUSED_TIMERS"):  # development aid: per-role cycle counters in the fused kernel
         flags.append("-DKWS_FUSED_TIMERS")
         force = True

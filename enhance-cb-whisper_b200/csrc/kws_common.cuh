@@ -92,6 +92,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint (ns): the thread is parked by the hardware until the phase completes or the
+// hint expires, instead of re-polling the barrier word through the shared-memory port every few dozen cycles
+// (the port is what the tensor core's operand reads saturate in the fused kernel).
+#ifndef KWS_WAIT_HINT_NS
+#define KWS_WAIT_HINT_NS 1000
+#endif
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)KWS_WAIT_HINT_NS)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug must surface as a trapped launch (CUDA error on
 // the host), never as a hung GPU.  ~4 s at 2 GHz.
 #ifndef KWS_WAIT_LIMIT_CYCLES
@@ -101,7 +120,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
+  while (!mbar_try_wait_hint(bar, parity)) {
     if ((++spins & 0x3ff) == 0 && clock64() - t0 > KWS_WAIT_LIMIT_CYCLES) {
       printf("[kws] mbarrier wait timeout: block %d thread %d tag %d parity %u\n", (int)blockIdx.x,
              (int)threadIdx.x, tag, parity);
