@@ -42,7 +42,7 @@
 // while this one is still being pulled), keep it as packed fp16 in registers and feed the ring one
 // quantum (4 rows) per stem step.
 //
-// TMEM: stem accumulators [0,128) and [128,256) (double-buffered), similarity region [256, 256+16C).
+// TMEM: stem accumulators [0,128) and [128,256) (double-buffered), similarity region [256, 256+16C), bias [448,512).
 // Roles (384 threads): warp 0 TMA producer, warp 1 stem MMA issuer, warp 2 TMEM allocator + similarity MMA
 // issuer (one elected thread each: two independent instruction streams into the one tensor pipe, so the
 // barrier polls of one never starve it), warps 4..7 stem epilogue (bf16 results staged in swizzled shared
@@ -93,7 +93,8 @@ constexpr int G_A_BYTES = 128 * 128;               // utt tile 128 px x 64 dims 
 __host__ __device__ constexpr int g_stage_bytes(int rows) { return G_A_BYTES + rows * 128; }
 constexpr int G_MAX_C = 12;
 constexpr int G_ACC_COLS = 128;                    // one stem accumulator: half a | half b
-constexpr int G_TMEM_SIM = 2 * G_ACC_COLS;         // similarity region starts at column 256
+constexpr int G_TMEM_SIM = 2 * G_ACC_COLS;         // similarity region starts at column 256 (<= 192 columns)
+constexpr int G_TMEM_BIAS = 448;                   // 64 columns: the folded-BN bias, replicated in every lane
 constexpr int G_OUT_STAGE = 4 * 32 * 128;          // per epilogue warp: 32 pixels x 64 bf16 (SW128), source of its TMA stores
 constexpr int G_NPAIR = G_MAX_C / 2;                 // similarity tiles are handed over per pair of layers
 constexpr int G_NBAR = 2 * G_NS + 2 * G_NPAIR + 4 + 4 + 2 + 2 + 4;
@@ -161,6 +162,15 @@ __device__ __forceinline__ uint64_t f32x2_of_f16x2(uint32_t h) {
   return pack_b64(__float_as_uint(f.x), __float_as_uint(f.y));
 }
 
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -210,7 +220,6 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
   uint64_t* aempty = afull + 2;           // [2] epilogue -> MMA
   uint64_t* pload = aempty + 2;           // [4] TMA load of the previous pass's partial sums -> epilogue warp
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + G_NBAR);
-  float* s_bias = reinterpret_cast<float*>(bars + G_NBAR + 2);  // [64]; L1 is carved down to nothing, keep it out of L2
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -222,7 +231,6 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
     // finite values, they only ever meet zero weights or discarded pixel slots
     for (int i = threadIdx.x; i < (G_RING_BYTES - 64) / 16; i += G_THREADS)  // the last block's pad holds the barriers
       reinterpret_cast<uint4*>(s_ring)[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (threadIdx.x < G_OC) s_bias[threadIdx.x] = __ldg(p.bias + threadIdx.x);
     if ((smem_u32(smem_raw) & 1023u) != 0) {
       if (threadIdx.x == 0) printf("[kws] dynamic shared memory base 0x%x is not 1024-byte aligned\n", smem_u32(smem_raw));
       __trap();
@@ -426,6 +434,19 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
     float* mbox0 = reinterpret_cast<float*>(s_ostage + (q | 1) * (32 * 128) + 28 * 128);
     float* mbox1 = mbox0 + 64;
     const CUtensorMap* my_map = lo_warp ? &map_out_lo : &map_out_hi;
+    // The bias lives in TMEM (64 columns, every lane holds all 64 values): with the whole L1 carved into shared
+    // memory a per-step bias read would cost either an L2 round trip or shared-memory port wavefronts.
+    {
+      const uint32_t t_bias = tmem_base + G_TMEM_BIAS + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t b[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) b[e] = __float_as_uint(__ldg(p.bias + ch * 16 + e));
+        tmem_st16(t_bias + ch * 16, b);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
     uint32_t acc_seq = 0;
     uint32_t pl_seq = 0;  // partial-sum tiles loaded so far by this warp (phase of pload[q])
     long long te_wait = 0, te_ld = 0, te_rest = 0;
@@ -455,11 +476,12 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
         uint8_t* srow = my_stage + lane * 128;
 #pragma unroll 1  // a real loop: the role loops are instruction-cache bound, not ILP bound
         for (int grp = 0; grp < 2; ++grp) {  // 32 output channels per TMEM round trip
-          uint32_t va[2][16], vb[2][16];
+          uint32_t va[2][16], vb[2][16], vbias[2][16];
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             tmem_ld16(t_row + G_OC + grp * 32 + h * 16, vb[h]);
             tmem_ld16(t_row + grp * 32 + h * 16, va[h]);
+            tmem_ld16(tmem_base + G_TMEM_BIAS + ((uint32_t)(q * 32) << 16) + grp * 32 + h * 16, vbias[h]);
           }
           if (grp == 0) {
             // the previous step's TMA store must have read this warp's staging buffer before it is reused
@@ -534,9 +556,8 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
                 uint64_t s0 = add_f32x2(pack_b64(va[h][e], va[h][e + 1]), pack_b64(vb[h][e], vb[h][e + 1]));
                 uint64_t s1 = add_f32x2(pack_b64(va[h][e + 2], va[h][e + 3]), pack_b64(vb[h][e + 2], vb[h][e + 3]));
                 if (with_bias) {
-                  const float4 b4 = *reinterpret_cast<const float4*>(s_bias + ch * 16 + e);
-                  s0 = add_f32x2(s0, pack_b64(__float_as_uint(b4.x), __float_as_uint(b4.y)));
-                  s1 = add_f32x2(s1, pack_b64(__float_as_uint(b4.z), __float_as_uint(b4.w)));
+                  s0 = add_f32x2(s0, pack_b64(vbias[h][e], vbias[h][e + 1]));
+                  s1 = add_f32x2(s1, pack_b64(vbias[h][e + 2], vbias[h][e + 3]));
                 }
                 if (add_prev) {
                   s0 = add_f32x2(s0, f32x2_of_f16x2(prev[e >> 1]));
@@ -555,11 +576,10 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
               float r[16];
 #pragma unroll
               for (int e = 0; e < 16; e += 4) {
-                const float4 b4 = *reinterpret_cast<const float4*>(s_bias + ch * 16 + e);
-                r[e] = fmaxf(__uint_as_float(va[h][e]) + __uint_as_float(vb[h][e]) + b4.x, 0.f);
-                r[e + 1] = fmaxf(__uint_as_float(va[h][e + 1]) + __uint_as_float(vb[h][e + 1]) + b4.y, 0.f);
-                r[e + 2] = fmaxf(__uint_as_float(va[h][e + 2]) + __uint_as_float(vb[h][e + 2]) + b4.z, 0.f);
-                r[e + 3] = fmaxf(__uint_as_float(va[h][e + 3]) + __uint_as_float(vb[h][e + 3]) + b4.w, 0.f);
+                r[e] = fmaxf(__uint_as_float(va[h][e]) + __uint_as_float(vb[h][e]) + __uint_as_float(vbias[h][e]), 0.f);
+                r[e + 1] = fmaxf(__uint_as_float(va[h][e + 1]) + __uint_as_float(vb[h][e + 1]) + __uint_as_float(vbias[h][e + 1]), 0.f);
+                r[e + 2] = fmaxf(__uint_as_float(va[h][e + 2]) + __uint_as_float(vb[h][e + 2]) + __uint_as_float(vbias[h][e + 2]), 0.f);
+                r[e + 3] = fmaxf(__uint_as_float(va[h][e + 3]) + __uint_as_float(vb[h][e + 3]) + __uint_as_float(vbias[h][e + 3]), 0.f);
               }
               if (ok) {
 #pragma unroll
@@ -704,7 +724,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
 
 constexpr size_t g_smem_bytes(int rows, int n_mma) {
   return (size_t)G_NS * g_stage_bytes(rows) + (size_t)7 * n_mma * G_MMA_W_BYTES + G_OUT_STAGE + G_RING_BYTES - 64 +
-         G_NBAR * 8 + 16 + G_OC * 4;
+         G_NBAR * 8 + 16;
 }
 static_assert(g_smem_bytes(16, 3) <= 232448 && g_smem_bytes(32, 2) <= 232448 && g_smem_bytes(48, 2) <= 232448,
               "fused kernel exceeds the 227 KB shared-memory limit");
