@@ -283,6 +283,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      [[maybe_unused]] uint32_t tr_stage = 0;
       for (long long it = blockIdx.x; it < p.num_items; it += gridDim.x) {
         const ItemCoord w = decode_item(p, it);
         const int jbase = 2 * G_TILE_OJ * w.ct - 3;  // input column of pixel x = 0 (OOB columns read as zero)
@@ -290,10 +291,13 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
           for (int c = 0; c < p.C; ++c) {
             for (int kb = 0; kb < p.nkb; ++kb) {
               mbar_wait(&oempty[stage], phase ^ 1, 100 + stage);
+              KWS_TRACE(3, tr_stage, 2);  // slot free seen by the producer
               uint8_t* sa = s_ops + stage * G_STAGE;
               mbar_arrive_expect_tx(&ofull[stage], G_STAGE);
               tma_load_3d(&map_utt, &ofull[stage], sa, kb * 64, jbase, (p.c0 + c) * p.U + w.u);
               tma_load_3d(&map_kwd, &ofull[stage], sa + G_A_BYTES, kb * 64, ROWS * n - 3, (p.c0 + c) * p.K + w.kw);
+              KWS_TRACE(3, tr_stage, 3);  // loads issued
+              ++tr_stage;
               if (++stage == G_NS) stage = 0, phase ^= 1;
             }
           }
@@ -310,6 +314,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
       const uint64_t sdesc0 = make_smem_desc(0, 16, 1024, LAYOUT_SW128);
       int o_stage = 0;
       uint32_t o_phase = 0, g = 0;
+      [[maybe_unused]] uint32_t tr_s = 0;
       for (long long it = blockIdx.x; it < p.num_items; it += gridDim.x) {
         for (int n = 0; n < p.n_chunks; ++n, ++g) {
           for (int st = 0; st < stages_per_chunk; ++st) {
@@ -320,6 +325,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
             if (st == 0) KWS_TRACE(2, g, 3);
             mbar_wait(&ofull[o_stage], o_phase, 300 + o_stage);
             if (st == 0) KWS_TRACE(2, g, 4);
+            KWS_TRACE(3, tr_s, 4);
             tc_fence_after();
             const uint32_t d = G_TMEM_SIM + c * ROWS;  // TMEM base is 0 (checked at start)
             const uint32_t sa = ops_u32 + o_stage * G_STAGE;
@@ -329,6 +335,8 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
             for (int k = 0; k < 4; ++k)
               umma_f16(d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc_sim, (kb | k) != 0);
             umma_commit(&oempty[o_stage]);
+            KWS_TRACE(3, tr_s, 5);
+            ++tr_s;
             if (++o_stage == G_NS) o_stage = 0, o_phase ^= 1;
             // layer pair complete (or last layer of an odd C): hand its tiles to the converters
             if (kb == p.nkb - 1 && ((c & 1) == 1 || c == p.C - 1)) umma_commit(&sfull[c >> 1]);

@@ -40,3 +40,9 @@ for s in range(2 * nP, 5 * nP):  # items 2..4 of CTA 0 (steady state)
 print("chunk | sim issuer: start, +sempty0 wait, +ofull wait, last stage issued(+) | converter: first seen, pulled(+) | quanta: slot_free stored(+)")
 for c in range(20, 32):
     print(f"chunk {c}: sim {chk[c,2]-t0:8d} +{chk[c,3]-chk[c,2]:5d} +{chk[c,4]-chk[c,3]:5d} +{chk[c,5]-chk[c,4]:5d} | conv {chk[c,0]-t0:8d} +{chk[c,1]-chk[c,0]:5d}   " + "  ".join(f"q{4*c+j}: {qua[4*c+j,0]-t0:8d} +{qua[4*c+j,1]-qua[4*c+j,0]:4d}" for j in range(4)))
+
+print("stage | producer: slot free seen, +loads issued | sim issuer: operands seen (TMA latency from issue), +MMAs issued | slot round trip")
+for i in range(300, 340):
+    pf, pi, so, sm = qua[i, 2] - t0, qua[i, 3] - t0, qua[i, 4] - t0, qua[i, 5] - t0
+    nxt = qua[i + 3, 2] - t0
+    print(f"stage {i}: prod {pf:8d} +{pi - pf:4d} | sim {so:8d} (tma {so - pi:5d}) +{sm - so:4d} | commit->slot free seen {nxt - sm:5d} | round trip {qua[i+3,4]-qua[i,4]:5d}")
