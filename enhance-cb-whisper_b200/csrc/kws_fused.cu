@@ -679,9 +679,13 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
         const long long c2 = KWS_CLK();
         if (warp == 8 && lane == 0) KWS_TRACE(2, g, 1);
         tc_sfull += c1 - c0, tc_ld += c2 - c1;
+        // 16 rows (4 quanta) per trip of a real loop: the row registers are shifted down by 16 after each trip, so
+        // the store code exists once (static register indices, small instruction footprint) for any chunk height
+#pragma unroll 1
+        for (int q16 = 0; q16 < QPC; q16 += 4) {
 #pragma unroll
-        for (int qq = 0; qq < QPC; ++qq) {
-          if (qq < nq) {
+        for (int qq = 0; qq < 4; ++qq) {
+          if (q16 + qq < nq) {
             const long long c3 = KWS_CLK();
             mbar_wait(&qempty[Gq & 3], ((Gq >> 2) & 1) ^ 1, 800 + (int)(Gq & 3));
             const long long c4 = KWS_CLK();
@@ -713,6 +717,13 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
             ++Gq;
             tc_qempty += c4 - c3, tc_st += KWS_CLK() - c4;
           }
+        }
+        if (ROWS > 16) {
+#pragma unroll
+          for (int r = 0; r + 16 < ROWS; ++r)
+#pragma unroll
+            for (int j = 0; j < NPAIR; ++j) h2[r][j] = h2[r + 16][j];
+        }
         }
       }
     }
