@@ -538,8 +538,9 @@ def run_b200_arm(args, wl):
         e2e = {"value": world * K * Ue / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
                "batch": f"{K} keywords x {Ue} utterances per GPU per step",
-               "scope": "pinned host fp32 embeddings -> H2D -> compression -> similarity+stem -> HF ResNet-50 body "
-                        "+ head (cuDNN bf16, third-party) -> scores, detections, top-10 -> D2H",
+               "scope": "pinned host fp32 embeddings -> H2D -> compression -> similarity+stem -> max-pool -> ResNet-50 "
+                        "body + head (third-party: cuDNN bf16 fused conv+bias+ReLU, BatchNorms folded) -> scores, "
+                        "detections, top-10 -> D2H",
                "kws_launches_per_step": (ops.LAUNCHES - l0) / args.steps,
                "detections": int(h_det.sum().item())}
 

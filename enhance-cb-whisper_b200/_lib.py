@@ -12,7 +12,7 @@ import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libkws_b200.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # constants of include/kws_b200.h
 F16, BF16 = 0, 1
@@ -44,6 +44,7 @@ SIGNATURES = {
     "kws_sim_stem_supported": (_i, [_i, _i, _i, _i]),
     "kws_sim_stem_range": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "kws_resize_bilinear": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "kws_maxpool_nhwc": (_i, [_vp, C.c_longlong, _i, _i, _i, _vp, _vp]),
     "kws_scores": (_i, [_vp, _vp, _sz, _f, _vp, _vp, _vp]),
     "kws_topk": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
 }

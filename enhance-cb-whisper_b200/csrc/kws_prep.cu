@@ -340,6 +340,53 @@ __global__ void __launch_bounds__(256) topk_kernel(const float* __restrict__ sco
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// MaxPool2d(kernel 3, stride 2, padding 1) on a channels-last bf16 activation: the op that follows the
+// stem in the reference (HF modeling_resnet.py ResNetEmbeddings.pooler via src/efficient_kws/resnet.py:53).
+// HBM-bound: one thread = one pooled pixel x 8 channels (16 bytes); the nine taps of neighbouring pixels
+// overlap and are served by L1/L2, so DRAM sees each input byte once.  Out-of-image taps are skipped
+// (== the -inf padding of the reference); NaNs propagate like torch's max_pool2d.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint4 max_bf16x8(uint4 a, uint4 b) {
+  uint4 r;
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+  __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pr[i] = __hmax2_nan(pa[i], pb[i]);
+  return r;
+}
+
+__global__ void __launch_bounds__(256) maxpool_nhwc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
+                                                           long long N, int H, int W, int C8, int Hp, int Wp) {
+  const long long total = N * Hp * Wp * C8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % C8);
+    long long q = i / C8;
+    const int pj = (int)(q % Wp);
+    q /= Wp;
+    const int pi = (int)(q % Hp);
+    const long long n = q / Hp;
+    const uint4* img = in + n * H * W * C8 + ch;
+    const int r0 = 2 * pi, c0 = 2 * pj;  // centre tap: always inside the image
+    uint4 m = __ldg(img + ((long long)r0 * W + c0) * C8);
+#pragma unroll
+    for (int dr = -1; dr <= 1; ++dr) {
+      const int r = r0 + dr;
+      if (r < 0 || r >= H) continue;
+#pragma unroll
+      for (int dc = -1; dc <= 1; ++dc) {
+        const int c = c0 + dc;
+        if ((dr == 0 && dc == 0) || c < 0 || c >= W) continue;
+        m = max_bf16x8(m, __ldg(img + ((long long)r * W + c) * C8));
+      }
+    }
+    out[i] = m;
+  }
+}
+
 }  // namespace kws
 
 using namespace kws;
@@ -428,6 +475,23 @@ int kws_cast_f32_to_16(const float* src, void* dst16, size_t n, int dtype16, voi
   size_t blocks = (n + 255) / 256;
   if (blocks > 4096) blocks = 4096;
   cast16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(src, (uint16_t*)dst16, n, dtype16 == KWS_BF16);
+  KWS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int kws_maxpool_nhwc(const void* in_bf16, long long N, int H, int W, int C, void* out_bf16, void* stream) {
+  KWS_CHECK_ARG(in_bf16 && out_bf16, "maxpool: null pointer");
+  KWS_CHECK_ARG(N > 0 && H > 0 && W > 0, "maxpool: non-positive dimension");
+  KWS_CHECK_ARG(C > 0 && C % 8 == 0, "maxpool: C=%d must be a multiple of 8 (16-byte channel chunks)", C);
+  KWS_CHECK_ARG(((reinterpret_cast<uintptr_t>(in_bf16) | reinterpret_cast<uintptr_t>(out_bf16)) & 15) == 0,
+                "maxpool: pointers must be 16-byte aligned");
+  const int Hp = (H + 1) / 2, Wp = (W + 1) / 2;
+  const long long total = N * Hp * Wp * (C / 8);
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)sm_count() * 32;  // grid-stride: 8 resident CTAs per SM, 4 waves
+  if (blocks > cap) blocks = cap;
+  maxpool_nhwc_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(in_bf16), reinterpret_cast<uint4*>(out_bf16), N, H, W, C / 8, Hp, Wp);
   KWS_CUDA(cudaGetLastError());
   return 0;
 }

@@ -31,6 +31,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
+from .body import FusedBody
 from .engine import KWSEngine, PackedWeights, pack_weights
 
 
@@ -98,7 +99,8 @@ class B200ForwardMixin:
     and, for LE/LEF, ``self.projector`` / ``self.time_projector``."""
 
     # options (set through **kwargs ``b200_*`` or attributes)
-    b200_body_dtype: str = "float32"  # "float32" (parity) | "bfloat16" (throughput, channels_last)
+    b200_body_dtype: str = "float32"  # "float32" (parity, unmodified HF modules) | "bfloat16" (throughput: folded
+    #                                     BN + cuDNN fused convolutions, channels_last) | "bfloat16_unfused"
     b200_return_features: bool = True  # materialise KWSOutput.features (fp32) like the reference
     b200_layer_idx: Optional[Sequence[int]] = None  # explicit layer selection into the given stack
     b200_mlp_dtype: str = "float16"  # projector GEMM operands: "float16" (parity) | "bfloat16" (range-safe)
@@ -143,11 +145,21 @@ class B200ForwardMixin:
     def _body(self, stem_act: torch.Tensor) -> torch.Tensor:
         if self.b200_body_dtype == "float32":
             return run_body(self.model, stem_act)
-        if self._body_lowp is None:
-            m = copy.deepcopy(self.model).to(dtype=torch.bfloat16, memory_format=torch.channels_last)
-            m.classifier.float()
-            self._body_lowp = m.eval()
-        return run_body(self._body_lowp, stem_act)
+        kind = self.b200_body_dtype
+        if kind not in ("bfloat16", "bfloat16_unfused"):
+            raise ValueError(f"b200_body_dtype must be float32 | bfloat16 | bfloat16_unfused, got {kind!r}")
+        if self._body_lowp is None or self._body_lowp[0] != kind:
+            if kind == "bfloat16_unfused":  # the unmodified HF modules, cast (A/B reference of "bfloat16")
+                m = copy.deepcopy(self.model).to(dtype=torch.bfloat16, memory_format=torch.channels_last)
+                m.classifier.float()
+                self._body_lowp = (kind, m.eval())
+            else:
+                self._body_lowp = (kind, FusedBody(self.model, torch.bfloat16))
+        if kind == "bfloat16_unfused":
+            return run_body(self._body_lowp[1], stem_act)
+        # "bfloat16": BatchNorms folded, one cuDNN fused conv+bias(+residual)+ReLU per convolution (body.py);
+        # max-pool in libkws_b200 (HBM-bound kernel; torch's channels-last bf16 max_pool2d runs at ~0.7 TB/s)
+        return self._body_lowp[1](ops.maxpool_nhwc(stem_act), pooled=True)
 
     # ---- the reference-facing call -------------------------------------------------
     def forward(self, kwd_features: torch.Tensor, utt_features: torch.Tensor, labels: torch.Tensor = None,

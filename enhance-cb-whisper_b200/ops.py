@@ -296,6 +296,26 @@ def resize_bilinear(feat_f32: torch.Tensor, src_h: Optional[torch.Tensor], size:
     return o32, o16
 
 
+def maxpool_nhwc(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """MaxPool2d(3, 2, 1) of a channels-last bf16 activation (logical [N,C,H,W], physical [N,H,W,C]) ->
+    channels-last bf16 [N,C,ceil(H/2),ceil(W/2)]; bit-identical to F.max_pool2d."""
+    lib = _lib.load()
+    if x.dim() != 4:
+        raise KWSError(f"maxpool_nhwc expects [N,C,H,W], got {tuple(x.shape)}")
+    N, Cc, H, W = x.shape
+    phys = x.permute(0, 2, 3, 1)
+    if not phys.is_contiguous():
+        raise KWSError("maxpool_nhwc needs a channels_last (NHWC-contiguous) tensor")
+    Hp, Wp = (H + 1) // 2, (W + 1) // 2
+    if out is None:
+        out = torch.empty((N, Hp, Wp, Cc), dtype=torch.bfloat16, device=x.device)
+    elif out.dtype != torch.bfloat16 or out.numel() < N * Hp * Wp * Cc:
+        raise KWSError("maxpool_nhwc: out buffer too small / wrong dtype")
+    check(lib.kws_maxpool_nhwc(_cuda(phys, "x", torch.bfloat16), N, H, W, Cc, _cuda(out, "out"), _stream()),
+          "kws_maxpool_nhwc")
+    return out.view(-1)[: N * Hp * Wp * Cc].view(N, Hp, Wp, Cc).permute(0, 3, 1, 2)
+
+
 # ---- scores ------------------------------------------------------------------------
 def scores(logits: torch.Tensor, hotword_mask: Optional[torch.Tensor], threshold: float):
     """logits fp32 [n,2] -> (scores fp32 [n], detections uint8 [n])"""

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define KWS_ABI_VERSION 5
+#define KWS_ABI_VERSION 6
 
 /* 16-bit operand formats (same encoding as the tcgen05 kind::f16 descriptor) */
 #define KWS_F16 0  /* IEEE half: 10-bit mantissa; for L2-normalised data and sane weights */
@@ -182,6 +182,12 @@ int kws_sim_stem_range(const void* kwd_n, const void* utt_n, int C, int K, int U
  *   Requires U*C <= 65535 (whole keywords per launch).                                           */
 int kws_resize_bilinear(const float* feat_f32, const int32_t* src_h, int K, int U, int C, int Hs, int Ws, int Ho, int Wo,
                         float* out_f32, void* out_f16, int pitch16, void* stream);
+
+/* MaxPool2d(3, stride 2, padding 1) on the channels-last bf16 stem activation: the first op of the ResNet
+ * body (HF modeling_resnet.py ResNetEmbeddings.pooler, reached through src/efficient_kws/resnet.py:53).
+ * Bit-identical to torch's max_pool2d (max is exact; NaNs propagate).
+ *   in  bf16 [N,H,W,C], out bf16 [N,ceil(H/2),ceil(W/2),C]; C % 8 == 0                              */
+int kws_maxpool_nhwc(const void* in_bf16, long long N, int H, int W, int C, void* out_bf16, void* stream);
 
 /* ---- scores ---------------------------------------------------------------- */
 

@@ -20,7 +20,7 @@ def declared_symbols():
 def test_header_declares_expected_entry_points():
     syms = declared_symbols()
     for s in ("kws_abi_version", "kws_last_error", "kws_normalize_rows", "kws_mlp", "kws_temporal", "kws_sim",
-              "kws_stem", "kws_scores", "kws_topk"):
+              "kws_stem", "kws_sim_stem", "kws_maxpool_nhwc", "kws_scores", "kws_topk"):
         assert s in syms
 
 
@@ -64,6 +64,9 @@ def test_bad_arguments_are_rejected_without_a_device(built_lib):
     # MLP shape rules
     assert lib.kws_mlp(one, 1, 1, 1, 100, 50, 64, 0, one, one, one, one, one, None, 1e-6, 0, one, None) == -1
     assert b"multiple of 64" in lib.kws_last_error()
+    # max-pool: channel chunks of 16 bytes
+    assert lib.kws_maxpool_nhwc(one, 1, 4, 4, 12, one, None) == -1
+    assert b"multiple of 8" in lib.kws_last_error()
     # top-k limits
     assert lib.kws_topk(one, None, 10, 1, 0, 2000, one, one, None) == -1
     with pytest.raises(_lib.KWSError):

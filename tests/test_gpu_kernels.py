@@ -257,6 +257,22 @@ def test_sim_stem_range_is_a_block_of_the_full_job(ops, cuda_dev):
         ops.sim_stem(kn, un, wp, bias, ops.STEM_OUT_NCHW_F32, k_range=(5, 9))
 
 
+# ---- max-pool that follows the stem -----------------------------------------------------------------
+@pytest.mark.parametrize("N,Cc,H,W", [(1, 64, 1, 1), (2, 64, 7, 9), (3, 64, 38, 375), (2, 64, 75, 750), (2, 8, 12, 5)])
+def test_maxpool_nhwc_is_bit_identical_to_torch(ops, cuda_dev, N, Cc, H, W):
+    """MaxPool2d(3,2,1) (HF ResNetEmbeddings.pooler) on the channels-last bf16 stem activation: exact."""
+    g = gen(cuda_dev)
+    x = torch.randn(N, H, W, Cc, generator=g, device=cuda_dev).to(torch.bfloat16).permute(0, 3, 1, 2)
+    got = ops.maxpool_nhwc(x)
+    exp = torch.nn.functional.max_pool2d(x.float(), 3, 2, 1)
+    assert got.shape == exp.shape and got.dtype == torch.bfloat16
+    assert got.permute(0, 2, 3, 1).is_contiguous()
+    assert torch.equal(got.float(), exp)
+    if H * W > 1:
+        with pytest.raises(Exception):  # NCHW-contiguous input is refused, not silently re-laid out
+            ops.maxpool_nhwc(x.contiguous())
+
+
 # ---- scores + top-k -------------------------------------------------------------------------------
 def test_scores_and_detections(ops, cuda_dev):
     g = gen(cuda_dev)

@@ -168,3 +168,37 @@ def test_lef_many_layers_runs_fused_in_passes(built_lib, cuda_dev):
     eng.hot_path(kn, un, ops.STEM_OUT_NHWC_BF16, max_pairs=K * U, consume=lambda *a: got.append(a[-1].float().clone()))
     assert got[0].shape == exp.shape
     assert err(got[0], exp) <= 2e-2 * max(1.0, exp.abs().max().item() / 4)
+
+
+def test_throughput_body_matches_unfused_modules(built_lib, cuda_dev):
+    """b200_body_dtype="bfloat16": BatchNorms folded + cuDNN fused conv+bias(+residual)+ReLU + kws_maxpool_nhwc
+    (body.py) against the unmodified HF modules run in fp32 on the same bf16 stem activation, and against the
+    same modules cast to bf16 ("bfloat16_unfused"): the folded path must be no further from fp32 than the
+    cast modules are (plus slack), and detections on clear margins agree."""
+    import enhance_cb_whisper_b200 as kb
+    from enhance_cb_whisper_b200 import ops
+    from enhance_cb_whisper_b200.model import run_body
+
+    m, meta, x, outs, _ = build("LE_small", cuda_dev, b200_body_dtype="bfloat16")
+    eng = m.prepare(cuda_dev)
+    kn, un = eng.compress(x["kwd"], x["km"]), eng.compress(x["utt"], x["um"])
+    st = []
+    eng.hot_path(kn, un, ops.STEM_OUT_NHWC_BF16, max_pairs=64, consume=lambda *a: st.append(a[-1].clone()))
+    st = torch.cat(st)
+    ref32 = run_body(m.model, st.float())
+    fused = m._body(st)
+    assert fused.dtype == torch.float32 and fused.shape == ref32.shape
+    m.b200_body_dtype = "bfloat16_unfused"
+    cast = m._body(st)
+    m.b200_body_dtype = "bfloat16"
+    scale = max(1.0, ref32.abs().max().item())
+    e_fused, e_cast = err(fused, ref32) / scale, err(cast, ref32) / scale
+    assert e_fused <= max(2.0 * e_cast, 2e-2), (e_fused, e_cast)
+    # scores through the public call
+    sc, det, logits = m.score(x["kwd"], x["utt"], x["km"], x["um"], hotword_mask=x["hot"])
+    gold = outs["scores"]
+    clear = (gold - 0.5).abs() > 0.1
+    assert torch.equal(det.cpu().bool()[clear], (gold >= 0.5)[clear])
+    with pytest.raises(ValueError):
+        m.b200_body_dtype = "int8"
+        m._body(st)
