@@ -110,6 +110,8 @@ class B200ForwardMixin:
         self._packed_key = None
         self._engine: Optional[KWSEngine] = None
         self._body_lowp = None
+        self._copy_stream = None
+        self._stage = {}
 
     # ---- variant / weights ---------------------------------------------------------
     @property
@@ -220,6 +222,72 @@ class B200ForwardMixin:
         kwd_n = eng.compress(kwd_features, kwd_mask, layer_idx)
         utt_n = eng.compress(utt_features, utt_mask, layer_idx)
         return self.score_compressed(kwd_n, utt_n, hotword_mask, max_pairs, threshold)
+
+    @torch.no_grad()
+    def score_host(self, kwd_features, utt_features, kwd_mask, utt_mask, hotword_mask=None, max_pairs: int = 256,
+                   threshold: Optional[float] = None, kwd_slab: int = 125, device=None):
+        """``score`` for inputs that live in (pinned) HOST memory -- what the reference's DataLoader hands to
+        ``test_step`` (model.py:749-765).  The keyword bank is uploaded slab by slab on a copy stream into two
+        staging buffers while the previous slab is compressed and scored on the current stream, so the PCIe
+        transfer of the raw fp32 embeddings (the largest tensor of the job: K x C x Tk x D x 4 bytes) hides
+        behind the compute.  Returns device tensors like ``score``."""
+        dev = torch.device(device) if device is not None else next(self.parameters()).device
+        eng = self.prepare(dev)
+        layer_idx = list(self.b200_layer_idx) if self.b200_layer_idx is not None else list(range(self.hparams.n_layers))
+        K, U = kwd_features.shape[0], utt_features.shape[0]
+        cur = torch.cuda.current_stream(dev)
+        if getattr(self, "_copy_stream", None) is None or self._copy_stream.device != dev:
+            self._copy_stream = torch.cuda.Stream(dev)
+            self._stage = {}
+        cs = self._copy_stream
+        slab = max(1, min(int(kwd_slab), K))
+        key = (slab,) + tuple(kwd_features.shape[1:]) + tuple(kwd_mask.shape[1:])
+        if self._stage.get("key") != key:
+            self._stage = {"key": key,
+                           "kwd": [torch.empty((slab,) + tuple(kwd_features.shape[1:]), dtype=torch.float32, device=dev)
+                                   for _ in range(2)],
+                           "mask": [torch.empty((slab,) + tuple(kwd_mask.shape[1:]), dtype=torch.float32, device=dev)
+                                    for _ in range(2)],
+                           "free": [torch.cuda.Event() for _ in range(2)], "ready": [torch.cuda.Event() for _ in range(2)]}
+        stg = self._stage
+        utt_n = eng.compress(utt_features.to(dev, non_blocking=True), utt_mask.to(dev, non_blocking=True), layer_idx)
+        hot = hotword_mask.to(dev, non_blocking=True) if hotword_mask is not None else None
+        logits = torch.empty((K, U, 2), dtype=torch.float32, device=dev)
+        lowp = self.b200_body_dtype != "float32"
+        out_mode = ops.STEM_OUT_NHWC_BF16 if lowp else ops.STEM_OUT_NCHW_F32
+        for b in range(2):
+            stg["free"][b].record(cur)
+        n_slabs = (K + slab - 1) // slab
+
+        def upload(i):
+            b, k0 = i & 1, i * slab
+            k1 = min(K, k0 + slab)
+            cs.wait_event(stg["free"][b])
+            with torch.cuda.stream(cs):
+                stg["kwd"][b][: k1 - k0].copy_(kwd_features[k0:k1], non_blocking=True)
+                stg["mask"][b][: k1 - k0].copy_(kwd_mask[k0:k1], non_blocking=True)
+                stg["ready"][b].record(cs)
+
+        upload(0)
+        for i in range(n_slabs):
+            b, k0 = i & 1, i * slab
+            k1 = min(K, k0 + slab)
+            if i + 1 < n_slabs:
+                upload(i + 1)
+            cur.wait_event(stg["ready"][b])
+            kwd_n = eng.compress(stg["kwd"][b][: k1 - k0], stg["mask"][b][: k1 - k0], layer_idx)
+            stg["free"][b].record(cur)
+
+            def consume(a0, a1, u0, u1, st, k0=k0):
+                logits[k0 + a0:k0 + a1, u0:u1] = self._body(st).float().view(a1 - a0, u1 - u0, 2)
+
+            eng.hot_path(kwd_n, utt_n, out_mode, max_pairs, consume, bufs=stg.setdefault("bufs", {}))
+        hw = None
+        if hot is not None:
+            hw = hot.to(torch.float32).view(K, 1).expand(K, U).contiguous().view(-1)
+        thr = float(self.hparams.threshold if threshold is None else threshold)
+        sc, det = ops.scores(logits.view(-1, 2), hw, thr)
+        return sc.view(K, U), det.view(K, U), logits
 
     @torch.no_grad()
     def score_compressed(self, kwd_n, utt_n, hotword_mask=None, max_pairs: int = 256,

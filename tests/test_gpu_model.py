@@ -202,3 +202,20 @@ def test_throughput_body_matches_unfused_modules(built_lib, cuda_dev):
     with pytest.raises(ValueError):
         m.b200_body_dtype = "int8"
         m._body(st)
+
+
+@pytest.mark.parametrize("name", ["LE_small", "LEF_odd"])
+def test_score_host_streams_slabs_and_matches_score(built_lib, cuda_dev, name):
+    """score_host(): pinned host inputs, keyword slabs uploaded on a copy stream while the previous slab is
+    scored == score() on device-resident inputs (slab size not dividing K, twice to reuse the staging)."""
+    m, meta, x, outs, _ = build(name, cuda_dev)
+    pin = lambda t: t.cpu().contiguous().pin_memory()
+    h = {k: pin(v) for k, v in x.items()}
+    sc0, det0, lg0 = m.score(x["kwd"], x["utt"], x["km"], x["um"], hotword_mask=x["hot"], max_pairs=3)
+    for slab in (3, 1, meta["K"] + 5):
+        sc, det, lg = m.score_host(h["kwd"], h["utt"], h["km"], h["um"], hotword_mask=h["hot"], max_pairs=3,
+                                   kwd_slab=slab, device=cuda_dev)
+        assert sc.is_cuda and err(lg, lg0) <= 1e-4 and err(sc, sc0) <= 1e-5
+        assert err(lg, outs["logits"]) <= TOL
+        clear = (sc0 - 0.5).abs() > 1e-3
+        assert torch.equal(det[clear], det0[clear])

@@ -1,7 +1,7 @@
 """Small fixed workload that launches every hot-path kernel a few times (for ncu and first
 timings; not a benchmark -- bench.py is).  Shapes are cfg2-like slabs (LE, C=12, D=768).
 
-    python tools/prof_kernels.py [--pairs-k 16] [--utts 2] [--iters 3] [--only stem|sim|mlp|rows]
+    python tools/prof_kernels.py [--pairs-k 16] [--utts 2] [--iters 3] [--only stem|sim|mlp|rows|temporal|maxpool|fused]
 """
 from __future__ import annotations
 
@@ -41,7 +41,8 @@ def main():
     Cc, K, U, Tk, Tu, D, P = a.C, a.pairs_k, a.utts, 150, 1500, a.D, 64
     H = D // 2
     pairs = K * U
-    want = lambda s: not a.only or a.only == s
+    only = set(filter(None, a.only.split(",")))
+    want = lambda s: not only or s in only
 
     def unit(*shape):
         x = torch.randn(*shape, generator=g, device=dev)
@@ -64,6 +65,22 @@ def main():
             t = timeit(lambda: ops.mlp(x16, K, Tk, w1, b1, w2, b2, None, ops.MLP_OUT_NORM_F16), a.iters)
             fl = 2.0 * Cc * K * Tk * (D * H + H * P)
             print(f"mlp {Cc}x{K * Tk}x{D}: {t:.3f} ms -> {fl / t / 1e9:.1f} TFLOP/s")
+    if want("temporal"):
+        proj = torch.randn(Cc, K, Tk, P, generator=g, device=dev)
+        wf = torch.randn(Cc, 3, P, P, generator=g, device=dev) / (3 * P) ** 0.5
+        bf = torch.zeros(Cc, P, device=dev)
+        t = timeit(lambda: ops.temporal(proj, wf, bf, None), a.iters)
+        byt = proj.numel() * 4 + proj.numel() // 2 * 2
+        print(f"temporal {Cc}x{K}x{Tk}x{P}: {t:.3f} ms -> {byt / t / 1e6:.0f} GB/s, "
+              f"{2.0 * 3 * P * P * proj.numel() / P / t / 1e9:.1f} TFLOP/s (fp32 FMA)")
+    if want("maxpool"):
+        act = torch.rand(pairs, 75, 750, 64, generator=g, device=dev).to(torch.bfloat16).permute(0, 3, 1, 2)
+        t = timeit(lambda: ops.maxpool_nhwc(act), a.iters)
+        byt = act.numel() * 2 * 1.25
+        print(f"maxpool {pairs}x75x750x64: {t:.3f} ms -> {byt / t / 1e6:.0f} GB/s")
+        del act
+    if only and only <= {"rows", "mlp", "temporal", "maxpool"}:
+        return
     kn = unit(Cc, K, Tk, P).half()
     un = unit(Cc, U, Tu, P).half()
     pitch = ops.pitch_for(Tu)
