@@ -16,7 +16,7 @@ ABI_VERSION = 6
 
 # constants of include/kws_b200.h
 F16, BF16 = 0, 1
-MLP_OUT_NORM_F16, MLP_OUT_RAW_F32 = 0, 1
+MLP_OUT_NORM_F16, MLP_OUT_RAW_F32, MLP_OUT_RAW_16 = 0, 1, 2
 PAIRS_ALL, PAIRS_DIAG = 0, 1
 STEM_OUT_NCHW_F32, STEM_OUT_NHWC_BF16 = 0, 1
 
@@ -31,12 +31,12 @@ SIGNATURES = {
     "kws_stem_weight_bytes": (_sz, [_i]),
     "kws_pack_stem_fused": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp]),
     "kws_stem_fused_weight_bytes": (_sz, [_i]),
-    "kws_fold_temporal_weights": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _vp, _vp, _vp]),
+    "kws_fold_temporal_weights": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp, _vp, _vp]),
     "kws_cast_f32_to_16": (_i, [_vp, _vp, _sz, _i, _vp]),
     "kws_normalize_rows": (_i, [_vp, _i, _i, _i, _i, C.POINTER(C.c_int32), _i, _vp, _f, _vp, _vp]),
     "kws_cast_rows16": (_i, [_vp, _i, _i, _i, _i, C.POINTER(C.c_int32), _i, _i, _vp, _vp]),
     "kws_mlp": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp]),
-    "kws_temporal": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp, _vp]),
+    "kws_temporal": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp, _vp]),
     "kws_sim": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "kws_stem": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "kws_stem_workspace_bytes": (_sz, [_i, _i, _i, _i]),

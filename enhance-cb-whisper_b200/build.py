@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libkws_b200.so")
 OBJ_DIR = os.path.join(HERE, "build")
-SOURCES = ["kws_abi.cu", "kws_prep.cu", "kws_gemm.cu", "kws_stem.cu", "kws_fused.cu"]
+SOURCES = ["kws_abi.cu", "kws_prep.cu", "kws_gemm.cu", "kws_temporal.cu", "kws_stem.cu", "kws_fused.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

@@ -47,7 +47,7 @@ struct GemmParams {
   const float* bias;  // [C, cols]
   const float* mask;  // EPI 1 normalised: [B, C, T] or null
   int out_mode;       // EPI 1: KWS_MLP_OUT_*
-  int hidden_bf16;    // EPI 0: hidden stored as bf16 (else saturating fp16)
+  int hidden_bf16;    // EPI 0 / RAW_16: 16-bit outputs stored as bf16 (else saturating fp16)
   int T, Cn;          // EPI 1 mask indexing: row r -> (b = r / T, t = r % T); Cn = layers
   float eps;
   // SIM
@@ -250,6 +250,25 @@ kws_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
               }
             }
           }
+        } else if (p.out_mode == KWS_MLP_OUT_RAW_16) {
+          // un-normalised 16-bit rows for the temporal projector (fp16 saturates instead of overflowing)
+          uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + ((long long)w.c * p.rows + row) * p.cols;
+          for (int ch = 0; ch < n_chunks; ++ch) {
+            tmem_ld16(t_row + ch * 16, v);
+            tmem_ld_wait();
+            if (row_ok) {
+              uint32_t pk[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float a = __uint_as_float(v[2 * e]) + __ldg(bias + ch * 16 + 2 * e);
+                const float b = __uint_as_float(v[2 * e + 1]) + __ldg(bias + ch * 16 + 2 * e + 1);
+                pk[e] = p.hidden_bf16 ? pack_bf162(a, b) : pack_half2_sat(a, b);
+              }
+              uint4* dst = reinterpret_cast<uint4*>(o + ch * 16);
+              dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+          }
         } else {
           // pass 1: squared norm of the row; pass 2: re-read TMEM, scale, store
           float ss = 0.f;
@@ -356,8 +375,8 @@ int kws_mlp(const void* x16, int C, int B, int T, int D, int H, int P, int dtype
   KWS_CHECK_ARG(D % 64 == 0 && D >= 64, "mlp: D=%d must be a multiple of 64", D);
   KWS_CHECK_ARG(H % 64 == 0 && H >= 64, "mlp: H=%d must be a multiple of 64", H);
   KWS_CHECK_ARG(P % 16 == 0 && P >= 16 && P <= 256, "mlp: P=%d must be a multiple of 16 in [16,256]", P);
-  KWS_CHECK_ARG(out_mode == KWS_MLP_OUT_NORM_F16 || out_mode == KWS_MLP_OUT_RAW_F32, "mlp: bad out_mode %d",
-                out_mode);
+  KWS_CHECK_ARG(out_mode == KWS_MLP_OUT_NORM_F16 || out_mode == KWS_MLP_OUT_RAW_F32 || out_mode == KWS_MLP_OUT_RAW_16,
+                "mlp: bad out_mode %d", out_mode);
   const long long R = (long long)B * T;
   KWS_CHECK_ARG(R < (1ll << 31), "mlp: B*T too large");
   cudaStream_t st = (cudaStream_t)stream;
@@ -402,6 +421,7 @@ int kws_mlp(const void* x16, int C, int B, int T, int D, int H, int P, int dtype
     p.bias = b2;
     p.mask = mask;
     p.out_mode = out_mode;
+    p.hidden_bf16 = dtype16 == KWS_BF16;
     p.T = T;
     p.Cn = C;
     p.eps = eps;

@@ -1,8 +1,7 @@
 // Operand preparation kernels (HBM-bound, CUDA cores):
 //   - normalize_rows : L variant -- layer selection + L2 normalise + mask + fp16
 //   - cast_rows_bf16 : LE/LEF    -- layer selection + bf16 cast, layer-major rows
-//   - temporal       : LEF       -- Conv1d(k3)+BN(folded)+MaxPool1d(3,2,1)+normalise
-//   - weight packing (stem BN fold + tap packing, temporal BN fold, bf16 cast)
+//   - weight packing (stem BN fold + tap packing, 16-bit casts); the LEF temporal projector is kws_temporal.cu
 // One warp owns one embedding row; every global access is a 128-bit (or the
 // widest aligned) coalesced vector access.
 #include "kws_common.cuh"
@@ -118,86 +117,6 @@ static int launch_rows(bool normalize, int dtype16, const float* x, int B, int C
 }
 
 // ---------------------------------------------------------------------------
-// LEF temporal projector.  proj fp32 [C,B,T,P] -> out fp16 [C,B,T2,P]
-// block = (tile of TT output frames, b, c); conv+BN rows staged in smem.
-// ---------------------------------------------------------------------------
-constexpr int TT = 32;  // pooled frames per block -> 2*TT+1 conv rows, 2*TT+3 input rows
-
-__global__ void __launch_bounds__(256) temporal_kernel(const float* __restrict__ proj, int C, int B, int T, int P,
-                                                       int T2, const float* __restrict__ wf,
-                                                       const float* __restrict__ bf, const float* __restrict__ mask,
-                                                       float eps, __half* __restrict__ out) {
-  extern __shared__ __align__(16) float sm[];
-  const int n_in = 2 * TT + 3, n_y = 2 * TT + 1;
-  float* s_w = sm;                  // [3][P][P]
-  float* s_x = s_w + 3 * P * P;     // [n_in][P]
-  float* s_y = s_x + n_in * P;      // [n_y][P]
-  const int c = blockIdx.z, b = blockIdx.y, t2_0 = blockIdx.x * TT;
-  const int tid = threadIdx.x;
-  const float* w_c = wf + (size_t)c * 3 * P * P;
-  for (int i = tid; i < 3 * P * P; i += blockDim.x) s_w[i] = w_c[i];
-  // input rows t = 2*t2_0 - 2 ... 2*t2_0 + 2*TT  (zero outside [0,T): Conv1d zero padding)
-  const float* x_cb = proj + ((size_t)c * B + b) * T * P;
-  const int t_in0 = 2 * t2_0 - 2;
-  for (int i = tid; i < n_in * P; i += blockDim.x) {
-    const int t = t_in0 + i / P;
-    s_x[i] = (t >= 0 && t < T) ? x_cb[(size_t)t * P + (i % P)] : 0.f;
-  }
-  __syncthreads();
-  // conv rows y[r] <-> t = 2*t2_0 - 1 + r, r in [0, n_y)
-  const int groups = blockDim.x / P;  // threads sharing one output channel stride over rows
-  const int po = tid % P, g = tid / P;
-  if (g < groups) {
-    const float bias = bf[c * P + po];
-    for (int r0 = g; r0 < n_y; r0 += groups * 4) {
-      float acc[4] = {bias, bias, bias, bias};
-      for (int kk = 0; kk < 3; ++kk) {
-        const float* wk = s_w + kk * P * P + po;
-        for (int pi = 0; pi < P; ++pi) {
-          const float w = wk[pi * P];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int r = r0 + q * groups;
-            if (r < n_y) acc[q] = fmaf(w, s_x[(r + kk) * P + pi], acc[q]);
-          }
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int r = r0 + q * groups;
-        if (r < n_y) s_y[r * P + po] = acc[q];
-      }
-    }
-  }
-  __syncthreads();
-  // MaxPool1d(3,2,1) (pads with -inf), L2 normalise over P, mask, fp16
-  const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-  for (int q = warp; q < TT; q += nwarps) {
-    const int t2 = t2_0 + q;
-    if (t2 >= T2) break;
-    float ss = 0.f;
-    float vals[8];  // P <= 256
-    int nv = 0;
-    for (int p = lane; p < P; p += 32, ++nv) {
-      float m = -INFINITY;
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        const int t = 2 * t2 - 1 + d;
-        if (t >= 0 && t < T) m = fmaxf(m, s_y[(2 * q + d) * P + p]);
-      }
-      vals[nv] = m;
-      ss += m * m;
-    }
-    ss = warp_sum(ss);
-    const float mk = mask ? mask[((size_t)b * C + c) * T2 + t2] : 1.f;
-    const float scale = mk / fmaxf(sqrtf(ss), eps);
-    __half* o = out + (((size_t)c * B + b) * T2 + t2) * P;
-    nv = 0;
-    for (int p = lane; p < P; p += 32, ++nv) o[p] = __float2half_rn(vals[nv] * scale);
-  }
-}
-
-// ---------------------------------------------------------------------------
 // weight packing
 // ---------------------------------------------------------------------------
 __global__ void pack_stem_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
@@ -218,22 +137,6 @@ __global__ void pack_stem_kernel(const float* __restrict__ w, const float* __res
   }
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < 64) bias[i] = beta[i] - mean[i] * gamma[i] / sqrtf(var[i] + eps);
-}
-
-__global__ void fold_temporal_kernel(const float* __restrict__ w, const float* __restrict__ cb,
-                                     const float* __restrict__ gamma, const float* __restrict__ beta,
-                                     const float* __restrict__ mean, const float* __restrict__ var, float eps,
-                                     int C, int P, float* __restrict__ wf, float* __restrict__ bf) {
-  const int total = C * 3 * P * P;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int po = i % P, pi = (i / P) % P, kk = (i / (P * P)) % 3, c = i / (3 * P * P);
-    const float s = gamma[c * P + po] / sqrtf(var[c * P + po] + eps);
-    wf[i] = w[(((size_t)c * P + po) * P + pi) * 3 + kk] * s;
-  }
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < C * P; i += gridDim.x * blockDim.x) {
-    const float s = gamma[i] / sqrtf(var[i] + eps);
-    bf[i] = (cb[i] - mean[i]) * s + beta[i];
-  }
 }
 
 __global__ void cast16_kernel(const float* __restrict__ s, uint16_t* __restrict__ d, size_t n, int bf16) {
@@ -404,24 +307,6 @@ int kws_cast_rows16(const float* x, int B, int Cin, int T, int D, const int32_t*
   return launch_rows(false, dtype16, x, B, Cin, T, D, layer_idx, C, nullptr, 0.f, out16, (cudaStream_t)stream);
 }
 
-int kws_temporal(const float* proj, int C, int B, int T, int P, const float* w_folded, const float* b_folded,
-                 const float* mask, float eps, void* out_f16, void* stream) {
-  KWS_CHECK_ARG(proj && w_folded && b_folded && out_f16, "temporal: null pointer");
-  KWS_CHECK_ARG(C > 0 && B > 0 && T > 0, "temporal: non-positive dimension");
-  KWS_CHECK_ARG(P > 0 && P <= 128 && 256 % P == 0, "temporal: P=%d must divide 256 and be <= 128", P);
-  KWS_CHECK_ARG(B <= 65535 && C <= 65535, "temporal: B,C must be <= 65535 per launch");
-  const int T2 = (T + 1) / 2;
-  const size_t smem = sizeof(float) * ((size_t)3 * P * P + (size_t)(2 * TT + 3) * P + (size_t)(2 * TT + 1) * P);
-  KWS_CHECK_ARG(smem <= 200 * 1024, "temporal: P=%d needs %zu bytes of shared memory", P, smem);
-  if (smem > 48 * 1024)
-    KWS_CUDA(cudaFuncSetAttribute(temporal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((T2 + TT - 1) / TT, B, C);
-  temporal_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(proj, C, B, T, P, T2, w_folded, b_folded, mask, eps,
-                                                            (__half*)out_f16);
-  KWS_CUDA(cudaGetLastError());
-  return 0;
-}
-
 int kws_resize_bilinear(const float* feat_f32, const int32_t* src_h, int K, int U, int C, int Hs, int Ws, int Ho, int Wo,
                         float* out_f32, void* out_f16, int pitch16, void* stream) {
   KWS_CHECK_ARG(feat_f32 && (out_f32 || out_f16), "resize: null pointer");
@@ -452,18 +337,6 @@ int kws_pack_stem_weights(const float* conv_w, const float* gamma, const float* 
   const int G = (C + 15) / 16;
   pack_stem_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(conv_w, gamma, beta, mean, var, eps, C, G,
                                                          (__half*)w_packed, bias);
-  KWS_CUDA(cudaGetLastError());
-  return 0;
-}
-
-int kws_fold_temporal_weights(const float* conv_w, const float* conv_b, const float* gamma, const float* beta,
-                              const float* mean, const float* var, float eps, int C, int P, float* w_folded,
-                              float* b_folded, void* stream) {
-  KWS_CHECK_ARG(conv_w && conv_b && gamma && beta && mean && var && w_folded && b_folded,
-                "fold_temporal: null pointer");
-  KWS_CHECK_ARG(C > 0 && P > 0, "fold_temporal: non-positive dimension");
-  fold_temporal_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(conv_w, conv_b, gamma, beta, mean, var, eps, C, P,
-                                                             w_folded, b_folded);
   KWS_CUDA(cudaGetLastError());
   return 0;
 }

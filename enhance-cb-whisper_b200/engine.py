@@ -33,7 +33,7 @@ class PackedWeights:
     b1: Optional[torch.Tensor] = None  # fp32 [C,H]
     w2: Optional[torch.Tensor] = None  # 16-bit [C,P,H]
     b2: Optional[torch.Tensor] = None  # fp32 [C,P]
-    wt: Optional[torch.Tensor] = None  # fp32 [C,3,P,P]  temporal conv, BN folded
+    wt: Optional[torch.Tensor] = None  # 16-bit [C,3,P/8,P,8]  temporal conv, BN folded, packed for kws_temporal
     bt: Optional[torch.Tensor] = None  # fp32 [C,P]
     stem_w: Optional[torch.Tensor] = None  # fp16 [G,49,2,64,8]
     stem_b: Optional[torch.Tensor] = None  # fp32 [64]
@@ -65,7 +65,7 @@ def pack_weights(sd: Mapping[str, torch.Tensor], variant: str, C: int, D: int, P
     if variant == "LEF":
         st = lambda name: torch.stack([dev(f"time_projector.{i}.{name}") for i in range(C)])
         pw.wt, pw.bt = ops.fold_temporal_weights(st("0.weight"), st("0.bias"), st("1.weight"), st("1.bias"),
-                                                 st("1.running_mean"), st("1.running_var"))
+                                                 st("1.running_mean"), st("1.running_var"), dtype16=mlp_dtype16)
     if STEM_KEY + "convolution.weight" in sd:
         pw.stem_w, pw.stem_b = ops.pack_stem_weights(
             dev(STEM_KEY + "convolution.weight"), dev(STEM_KEY + "normalization.weight"),
@@ -112,7 +112,7 @@ class KWSEngine:
         T2 = self.out_frames(T)
         out = torch.empty((w.C, B, T2, w.P), dtype=torch.float16, device=x.device)
         H = w.w1.shape[1]
-        per_item = w.C * T * (D + H) * 2 + w.C * T * w.P * 4
+        per_item = w.C * T * (D + H) * 2 + w.C * T * w.P * 2
         step = max(1, min(B, self.workspace_bytes // max(per_item, 1)))
         for b0 in range(0, B, step):
             b1 = min(B, b0 + step)
@@ -121,7 +121,7 @@ class KWSEngine:
             if w.variant == "LE":
                 o = ops.mlp(xb, b1 - b0, T, w.w1, w.b1, w.w2, w.b2, mb, ops.MLP_OUT_NORM_F16)
             else:
-                proj = ops.mlp(xb, b1 - b0, T, w.w1, w.b1, w.w2, w.b2, None, ops.MLP_OUT_RAW_F32)
+                proj = ops.mlp(xb, b1 - b0, T, w.w1, w.b1, w.w2, w.b2, None, ops.MLP_OUT_RAW_16)
                 o = ops.temporal(proj, w.wt, w.bt, mb)
             if step >= B:
                 return o

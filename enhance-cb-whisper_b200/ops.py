@@ -12,7 +12,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import (BF16, F16, MLP_OUT_NORM_F16, MLP_OUT_RAW_F32, PAIRS_ALL, PAIRS_DIAG, STEM_OUT_NCHW_F32,
+from ._lib import (BF16, F16, MLP_OUT_NORM_F16, MLP_OUT_RAW_16, MLP_OUT_RAW_F32, PAIRS_ALL, PAIRS_DIAG, STEM_OUT_NCHW_F32,
                    STEM_OUT_NHWC_BF16, KWSError)
 
 TORCH16 = {F16: torch.float16, BF16: torch.bfloat16}
@@ -91,15 +91,16 @@ def pack_stem_fused(conv_w, gamma, beta, mean, var, eps: float = BN_EPS) -> Tupl
     return wf, bias
 
 
-def fold_temporal_weights(conv_w, conv_b, gamma, beta, mean, var, eps: float = BN_EPS):
-    """conv_w [C,P,P,3] ... -> (w_folded fp32 [C,3,P,P], b_folded fp32 [C,P])"""
+def fold_temporal_weights(conv_w, conv_b, gamma, beta, mean, var, eps: float = BN_EPS, dtype16: int = F16):
+    """conv_w [C,P,P,3] ... -> (w16 packed fp16|bf16 [C,3,P/8,P,8], b_folded fp32 [C,P])"""
     lib = _lib.load()
     Cc, P = conv_w.shape[0], conv_w.shape[1]
     args = [t.detach().float().contiguous() for t in (conv_w, conv_b, gamma, beta, mean, var)]
-    wf = torch.empty((Cc, 3, P, P), dtype=torch.float32, device=conv_w.device)
+    wf = torch.empty((Cc, 3, P // 8, P, 8), dtype=TORCH16[dtype16], device=conv_w.device)
     bf = torch.empty((Cc, P), dtype=torch.float32, device=conv_w.device)
     check(lib.kws_fold_temporal_weights(*[_cuda(a, "temporal weight", torch.float32) for a in args], eps, Cc, P,
-                                        _cuda(wf, "wf"), _cuda(bf, "bf"), _stream()), "kws_fold_temporal_weights")
+                                        dtype16, _cuda(wf, "wf"), _cuda(bf, "bf"), _stream()),
+          "kws_fold_temporal_weights")
     return wf, bf
 
 
@@ -143,7 +144,7 @@ def cast_rows16(x: torch.Tensor, layer_idx: Sequence[int], dtype16: int = F16) -
 def mlp(x16: torch.Tensor, B: int, T: int, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor,
         b2: torch.Tensor, mask: Optional[torch.Tensor], out_mode: int, eps: float = SIM_EPS) -> torch.Tensor:
     """x [C,B*T,D]; w1 [C,H,D]; w2 [C,P,H] all fp16 or all bf16; b1 fp32 [C,H]; b2 fp32 [C,P]
-    -> fp16 [C,B,T,P] (normalised) or fp32 [C,B,T,P] (raw)."""
+    -> fp16 [C,B,T,P] (normalised), fp32 [C,B,T,P] (raw) or the operands' 16-bit type (raw, feeds temporal)."""
     lib = _lib.load()
     x_bf16 = x16
     dt = x16.dtype
@@ -157,8 +158,8 @@ def mlp(x16: torch.Tensor, B: int, T: int, w1: torch.Tensor, b1: torch.Tensor, w
     if tuple(w1.shape) != (Cc, H, D) or tuple(w2.shape) != (Cc, P, H):
         raise KWSError("projector weight shapes do not match x")
     hidden = torch.empty((Cc, R, H), dtype=dt, device=x_bf16.device)
-    out = torch.empty((Cc, B, T, P), dtype=torch.float16 if out_mode == MLP_OUT_NORM_F16 else torch.float32,
-                      device=x_bf16.device)
+    out_dt = {MLP_OUT_NORM_F16: torch.float16, MLP_OUT_RAW_F32: torch.float32, MLP_OUT_RAW_16: dt}[out_mode]
+    out = torch.empty((Cc, B, T, P), dtype=out_dt, device=x_bf16.device)
     check(lib.kws_mlp(_cuda(x_bf16, "x", dt), Cc, B, T, D, H, P, dtype16, _cuda(w1, "w1", dt),
                       _cuda(b1, "b1", torch.float32), _cuda(w2, "w2", dt),
                       _cuda(b2, "b2", torch.float32), _cuda(hidden, "hidden"),
@@ -166,19 +167,25 @@ def mlp(x16: torch.Tensor, B: int, T: int, w1: torch.Tensor, b1: torch.Tensor, w
     return out
 
 
-def temporal(proj: torch.Tensor, wf: torch.Tensor, bf: torch.Tensor, mask: Optional[torch.Tensor],
+def temporal(proj16: torch.Tensor, w16: torch.Tensor, bf: torch.Tensor, mask: Optional[torch.Tensor],
              eps: float = SIM_EPS) -> torch.Tensor:
-    """proj fp32 [C,B,T,P] -> fp16 [C,B,ceil(T/2),P]; mask fp32 [B,C,ceil(T/2)] or None."""
+    """proj fp16|bf16 [C,B,T,P] (mlp(..., MLP_OUT_RAW_16)) -> fp16 [C,B,ceil(T/2),P];
+    w16/bf from fold_temporal_weights (same 16-bit type); mask fp32 [B,C,ceil(T/2)] or None."""
     lib = _lib.load()
-    Cc, B, T, P = proj.shape
+    Cc, B, T, P = proj16.shape
     T2 = (T + 1) // 2
+    dt = proj16.dtype
+    if dt not in (torch.float16, torch.bfloat16) or w16.dtype != dt:
+        raise KWSError(f"proj/w16 must share one 16-bit dtype, got {proj16.dtype}/{w16.dtype}")
+    if tuple(w16.shape) != (Cc, 3, P // 8, P, 8):
+        raise KWSError(f"w16 must be [C,3,P/8,P,8]=({Cc},3,{P // 8},{P},8), got {tuple(w16.shape)}")
     if mask is not None and tuple(mask.shape) != (B, Cc, T2):
         raise KWSError(f"LEF mask must be at pooled resolution [B,C,ceil(T/2)]=({B},{Cc},{T2}), "
                        f"got {tuple(mask.shape)}")
-    out = torch.empty((Cc, B, T2, P), dtype=torch.float16, device=proj.device)
-    check(lib.kws_temporal(_cuda(proj, "proj", torch.float32), Cc, B, T, P, _cuda(wf, "wf", torch.float32),
-                           _cuda(bf, "bf", torch.float32), _cuda(mask, "mask", torch.float32), eps,
-                           _cuda(out, "out"), _stream()), "kws_temporal")
+    out = torch.empty((Cc, B, T2, P), dtype=torch.float16, device=proj16.device)
+    check(lib.kws_temporal(_cuda(proj16, "proj", dt), Cc, B, T, P, F16 if dt == torch.float16 else BF16,
+                           _cuda(w16, "w16", dt), _cuda(bf, "bf", torch.float32),
+                           _cuda(mask, "mask", torch.float32), eps, _cuda(out, "out"), _stream()), "kws_temporal")
     return out
 
 

@@ -42,7 +42,8 @@ extern "C" {
 
 /* kws_mlp out_mode */
 #define KWS_MLP_OUT_NORM_F16 0 /* LE : fp16 [C,R,P], row-normalised * mask          */
-#define KWS_MLP_OUT_RAW_F32 1  /* LEF: fp32 [C,R,P], un-normalised (feeds kws_temporal) */
+#define KWS_MLP_OUT_RAW_F32 1  /* fp32 [C,R,P], un-normalised (parity / inspection)     */
+#define KWS_MLP_OUT_RAW_16 2   /* LEF: dtype16 [C,R,P], un-normalised (feeds kws_temporal) */
 
 /* kws_sim pair_mode */
 #define KWS_PAIRS_ALL 0
@@ -79,14 +80,15 @@ int kws_pack_stem_fused(const float* conv_w, const float* gamma, const float* be
                         const float* var, float eps, int C, void* w_fused, float* bias, void* stream);
 size_t kws_stem_fused_weight_bytes(int C);
 
-/* Fold BatchNorm1d (eval) into the LEF temporal Conv1d.
+/* Fold BatchNorm1d (eval) into the LEF temporal Conv1d and pack it for kws_temporal.
  * time_projector[i] = Conv1d(P,P,3,pad 1) -> BatchNorm1d -> MaxPool1d(3,2,1)
  * (src/efficient_kws/model.py:107-124).
  *   conv_w fp32 [C,P,P,3], conv_b/gamma/beta/mean/var fp32 [C,P]
- *   w_folded fp32 [C,3,P(in),P(out)], b_folded fp32 [C,P]                      */
+ *   w16_packed fp16|bf16 [C,3,P/8,P(out),8(in)] (B operand of each tap, K-chunk-major: the kernel's
+ *   shared-memory image), b_folded fp32 [C,P].  P % 8 == 0.                     */
 int kws_fold_temporal_weights(const float* conv_w, const float* conv_b, const float* gamma, const float* beta,
-                              const float* mean, const float* var, float eps, int C, int P, float* w_folded,
-                              float* b_folded, void* stream);
+                              const float* mean, const float* var, float eps, int C, int P, int dtype16,
+                              void* w16_packed, float* b_folded, void* stream);
 
 /* fp32 -> fp16/bf16, saturating (projector Linear weights, src/efficient_kws/model.py:92-104) */
 int kws_cast_f32_to_16(const float* src, void* dst16, size_t n, int dtype16, void* stream);
@@ -119,11 +121,13 @@ int kws_mlp(const void* x16, int C, int B, int T, int D, int H, int P, int dtype
             int out_mode, void* out, void* stream);
 
 /* LEF temporal projector (BN folded) + MaxPool1d(3,2,1) + L2 normalisation +
- * mask folding (model.py:107-124, :152-166, :214-216, :187-191).
- *   proj fp32 [C,B,T,P] -> out fp16 [C,B,T2,P], T2 = ceil(T/2)
- *   mask fp32 [B,C,T2] (pooled resolution) or NULL                            */
-int kws_temporal(const float* proj, int C, int B, int T, int P, const float* w_folded, const float* b_folded,
-                 const float* mask, float eps, void* out_f16, void* stream);
+ * mask folding (model.py:107-124, :152-166, :214-216, :187-191) as a tcgen05 implicit GEMM over the
+ * frame axis (three taps = one shared-memory tile read at three row offsets).
+ *   proj16 fp16|bf16 [C,B,T,P] (kws_mlp, KWS_MLP_OUT_RAW_16) -> out fp16 [C,B,T2,P], T2 = ceil(T/2)
+ *   w16_packed / b_folded from kws_fold_temporal_weights (same dtype16)
+ *   mask fp32 [B,C,T2] (pooled resolution) or NULL.  P % 32 == 0, 32 <= P <= 128. */
+int kws_temporal(const void* proj16, int C, int B, int T, int P, int dtype16, const void* w16_packed,
+                 const float* b_folded, const float* mask, float eps, void* out_f16, void* stream);
 
 /* ---- per (keyword, utterance) pair ---------------------------------------- */
 

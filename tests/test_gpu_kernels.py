@@ -130,21 +130,41 @@ def test_mlp_matches_same_quantisation_reference(ops, cuda_dev, Cc, B, T, D, P, 
 
 
 # ---- LEF temporal projector -------------------------------------------------------------------
-@pytest.mark.parametrize("Cc,B,T,P", [(2, 3, 23, 64), (3, 2, 150, 64), (1, 1, 71, 32), (1, 2, 1, 64), (1, 1, 2, 64)])
-def test_temporal_matches_oracle(ops, cuda_dev, Cc, B, T, P):
+@pytest.mark.parametrize("d16", ["F16", "BF16"])
+@pytest.mark.parametrize("Cc,B,T,P", [(2, 3, 23, 64), (3, 2, 150, 64), (1, 1, 71, 32), (1, 2, 1, 64), (1, 1, 2, 64),
+                                      (2, 5, 124, 64), (1, 3, 125, 128), (2, 40, 150, 64)])
+def test_temporal_matches_oracle(ops, cuda_dev, Cc, B, T, P, d16):
+    """Conv1d(3)+BN+MaxPool1d(3,2,1)+normalise+mask as a tcgen05 implicit GEMM over flat frames (tiles of 126 rows
+    crossing item boundaries: T = 124, 125 put item edges on tile edges) vs the oracle's project_time on the same
+    16-bit-rounded projections, and vs the oracle fed 16-bit-rounded folded weights (tight)."""
     g = gen(cuda_dev)
+    dt = getattr(ops, d16)
     sd = O.make_weights("LEF", Cc, 128, P, seed=5)
-    proj = torch.randn(Cc, B, T, P, generator=g, device=cuda_dev)
+    proj = torch.randn(Cc, B, T, P, generator=g, device=cuda_dev).to(ops.TORCH16[dt])
     st = lambda n: torch.stack([sd[f"time_projector.{i}.{n}"] for i in range(Cc)]).to(cuda_dev)
     wf, bf = ops.fold_temporal_weights(st("0.weight"), st("0.bias"), st("1.weight"), st("1.bias"),
-                                       st("1.running_mean"), st("1.running_var"))
+                                       st("1.running_mean"), st("1.running_var"), dtype16=dt)
+    assert wf.shape == (Cc, 3, P // 8, P, 8) and wf.dtype == ops.TORCH16[dt]
     T2 = (T + 1) // 2
     mask = (torch.rand(B, Cc, T2, generator=g, device=cuda_dev) > 0.1).float()
     out = ops.temporal(proj, wf, bf, mask)
-    exp = torch.stack([O.project_time(proj[i].cpu(), sd, i) for i in range(Cc)]).to(cuda_dev)
-    exp = exp / exp.norm(dim=-1, keepdim=True).clamp(min=1e-6) * mask.permute(1, 0, 2)[..., None]
-    assert out.shape == (Cc, B, T2, P)
-    assert maxerr(out, exp) <= 1e-3
+    assert out.shape == (Cc, B, T2, P) and out.dtype == torch.float16
+    norm = lambda y: y / y.norm(dim=-1, keepdim=True).clamp(min=1e-6) * mask.permute(1, 0, 2)[..., None]
+    # (1) the reference arithmetic (fp32 weights) on the same rounded projections
+    exp = norm(torch.stack([O.project_time(proj[i].float().cpu(), sd, i) for i in range(Cc)]).to(cuda_dev))
+    assert maxerr(out, exp) <= (1e-2 if d16 == "BF16" else 2e-3)
+    # (2) same quantisation: folded weights rounded to the operand type, fp64 accumulation
+    s = st("1.weight") / torch.sqrt(st("1.running_var") + 1e-5)
+    wq = (st("0.weight") * s[:, :, None, None]).to(ops.TORCH16[dt]).double()  # [C,P,P,3]
+    bq = ((st("0.bias") - st("1.running_mean")) * s + st("1.bias")).double()
+    # the packed weights are exactly that rounding, re-laid out as [C,3,P/8,P(out),8(in)]
+    lay = wq.permute(0, 3, 2, 1).reshape(Cc, 3, P // 8, 8, P).permute(0, 1, 2, 4, 3)
+    assert maxerr(wf, lay) <= 2e-3 * lay.abs().max().item()  # same values up to one rounding step of s
+    wq = wf.double().permute(0, 1, 2, 4, 3).reshape(Cc, 3, P, P).permute(0, 3, 2, 1).contiguous()  # kernel's own
+    y = torch.stack([torch.nn.functional.conv1d(proj[i].double().transpose(1, 2), wq[i], bq[i], padding=1)
+                     for i in range(Cc)])
+    y = torch.nn.functional.max_pool1d(y.flatten(0, 1), 3, 2, 1).view(Cc, B, P, T2).transpose(2, 3)
+    assert maxerr(out, norm(y.float())) <= 6e-4  # fp16 output rounding (|v| <= 1) + fp32 accumulation order
 
 
 # ---- stem ---------------------------------------------------------------------------------------

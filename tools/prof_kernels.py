@@ -66,13 +66,14 @@ def main():
             fl = 2.0 * Cc * K * Tk * (D * H + H * P)
             print(f"mlp {Cc}x{K * Tk}x{D}: {t:.3f} ms -> {fl / t / 1e9:.1f} TFLOP/s")
     if want("temporal"):
-        proj = torch.randn(Cc, K, Tk, P, generator=g, device=dev)
-        wf = torch.randn(Cc, 3, P, P, generator=g, device=dev) / (3 * P) ** 0.5
-        bf = torch.zeros(Cc, P, device=dev)
+        proj = torch.randn(Cc, K, Tk, P, generator=g, device=dev).half()
+        cw = torch.randn(Cc, P, P, 3, generator=g, device=dev) / (3 * P) ** 0.5
+        one, zero = torch.ones(Cc, P, device=dev), torch.zeros(Cc, P, device=dev)
+        wf, bf = ops.fold_temporal_weights(cw, zero, one, zero, zero, one)
         t = timeit(lambda: ops.temporal(proj, wf, bf, None), a.iters)
-        byt = proj.numel() * 4 + proj.numel() // 2 * 2
+        byt = proj.numel() * 2 + proj.numel() // 2 * 2
         print(f"temporal {Cc}x{K}x{Tk}x{P}: {t:.3f} ms -> {byt / t / 1e6:.0f} GB/s, "
-              f"{2.0 * 3 * P * P * proj.numel() / P / t / 1e9:.1f} TFLOP/s (fp32 FMA)")
+              f"{2.0 * 3 * P * P * proj.numel() / P / t / 1e9:.1f} TFLOP/s")
     if want("maxpool"):
         act = torch.rand(pairs, 75, 750, 64, generator=g, device=dev).to(torch.bfloat16).permute(0, 3, 1, 2)
         t = timeit(lambda: ops.maxpool_nhwc(act), a.iters)
