@@ -53,6 +53,8 @@
 // 21 x 8 KB = 168 KB, similarity MMA operands 55 KB, TMA operand writes 55 KB, converter stores 16 KB,
 // epilogue staging 16 KB written + 16 KB read by the TMA store: ~340 KB = 2.7 k cycles, against 1.8 k
 // cycles of tensor math (21 x 64 + 12 x 39.5).  Measured: ~2.5 k cycles per step.
+#include <stdlib.h>
+
 #include "kws_common.cuh"
 #include "../../include/kws_b200.h"
 
@@ -84,7 +86,7 @@ constexpr int G_RING_BYTES = 8 * G_BLOCK;          // [k8 2][rp 2][plane 2]
 constexpr int G_MMA_W_BYTES = 2 * 128 * 16;        // 4096: one MMA's B operand [chunk 2][n 128][8 ch] fp16
 constexpr int G_MAX_MMA = 3;                       // stem MMAs per kernel row
 constexpr int G_W_BYTES = 7 * G_MAX_MMA * G_MMA_W_BYTES;  // 86016
-constexpr int G_NS = 3;                            // similarity operand stages
+constexpr int G_NS = 3;                            // similarity operand stages (single pass)
 constexpr int G_A_BYTES = 128 * 128;               // utt tile 128 px x 64 dims (SW128)
 // Similarity chunk = ROWS keyword frames per MMA (N = ROWS): 16 for up to 12 layers, 32 for <= 6, 48 for <= 4
 // (the TMEM region holds C x ROWS <= 192 columns, the converters C/2 x ROWS <= 96 packed registers).  Wide
@@ -97,7 +99,7 @@ constexpr int G_TMEM_SIM = 2 * G_ACC_COLS;         // similarity region starts a
 constexpr int G_TMEM_BIAS = 448;                   // 64 columns: the folded-BN bias, replicated in every lane
 constexpr int G_OUT_STAGE = 4 * 32 * 128;          // per epilogue warp: 32 pixels x 64 bf16 (SW128), source of its TMA stores
 constexpr int G_NPAIR = G_MAX_C / 2;                 // similarity tiles are handed over per pair of layers
-constexpr int G_NBAR = 2 * G_NS + 2 * G_NPAIR + 4 + 4 + 2 + 2 + 4;
+constexpr int G_NBAR = 2 * G_NS + 2 * G_NPAIR + 4 + 4 + 2 + 2 + 8;
 
 struct FusedParams {
   const uint4* w;     // fused stem weights (kws_pack_stem_fused)
@@ -115,6 +117,8 @@ struct FusedParams {
   int n_chunks;  // similarity chunks (ROWS input rows = ROWS/4 quanta) per item
   int w_bytes;   // bytes of this pass's stem weights in shared memory (7 * n_mma * 4096)
   int diag;
+  int prefetch;  // multi-pass partial sums of step n+1: 1 = loaded into a second staging set during step n;
+                 // 2 = pulled into L2 only (TMA prefetch), loaded and awaited in step n+1; 0 = neither
   long long num_items;
   long long* dbg;  // optional [grid][16] cycle counters (issuer 0-4, epilogue 5-7, converter 8-11; development aid), or null
 };
@@ -195,7 +199,8 @@ __device__ __forceinline__ ItemCoord decode_item(const FusedParams& p, long long
 
 // NHWC: bf16 channels-last through TMA stores; else fp32 NCHW with direct stores (parity).  ROWS: see above.
 // MULTI: channel-group passes (acc_mode 1..3) compiled in; single-pass launches use the leaner instance.
-template <bool NHWC, int ROWS, bool MULTI>
+// NHM: output channels / 16 per TMEM round trip of the multi-pass epilogue (1 | 2).
+template <bool NHWC, int ROWS, bool MULTI, int NHM = 2>
 __global__ void __launch_bounds__(G_THREADS, 1)
 kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_constant__ CUtensorMap map_kwd,
                  const __grid_constant__ CUtensorMap map_out_lo, const __grid_constant__ CUtensorMap map_out_hi,
@@ -205,20 +210,21 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
   constexpr int G_STAGE = g_stage_bytes(ROWS);
   constexpr int NPAIR = 96 / ROWS;                // layer pairs the converters can hold: 6 / 3 / 2
   constexpr int QPC = ROWS / 4;                   // quanta per similarity chunk
-  uint8_t* s_ops = base;                          // G_NS * G_STAGE (each 1024-aligned)
-  uint8_t* s_w = s_ops + G_NS * G_STAGE;          // p.w_bytes (multiple of 4096)
-  uint8_t* s_ostage = s_w + p.w_bytes;            // G_OUT_STAGE (4 x 4 KB, each 1024-aligned)
-  uint8_t* s_ring = s_ostage + G_OUT_STAGE;       // G_RING_BYTES
+  constexpr int NS = G_NS;                        // operand stages
+  uint8_t* s_ops = base;                          // NS * G_STAGE (each 1024-aligned)
+  uint8_t* s_w = s_ops + NS * G_STAGE;            // p.w_bytes (multiple of 4096)
+  uint8_t* s_ostage = s_w + p.w_bytes;            // G_OUT_STAGE (4 x 4 KB, each 1024-aligned); two sets when MULTI
+  uint8_t* s_ring = s_ostage + ((MULTI && p.prefetch == 1) ? 2 : 1) * G_OUT_STAGE;  // G_RING_BYTES
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + G_RING_BYTES - 64);  // from the last block's (unused) bank pad on
-  uint64_t* ofull = bars;                 // [G_NS] TMA -> MMA (similarity operands)
-  uint64_t* oempty = ofull + G_NS;        // [G_NS] MMA commit -> TMA
-  uint64_t* sfull = oempty + G_NS;        // [G_NPAIR] MMA commit -> converters (similarity tiles of a layer pair ready)
+  uint64_t* ofull = bars;                 // [NS] TMA -> MMA (similarity operands)
+  uint64_t* oempty = ofull + NS;          // [NS] MMA commit -> TMA
+  uint64_t* sfull = oempty + NS;          // [G_NPAIR] MMA commit -> converters (similarity tiles of a layer pair ready)
   uint64_t* sempty = sfull + G_NPAIR;     // [G_NPAIR] converters -> MMA (tiles pulled into registers)
   uint64_t* qfull = sempty + G_NPAIR;     // [4] converters -> MMA (ring quantum written)
   uint64_t* qempty = qfull + 4;           // [4] MMA commit -> converters
   uint64_t* afull = qempty + 4;           // [2] MMA commit -> epilogue (stem accumulator ready)
   uint64_t* aempty = afull + 2;           // [2] epilogue -> MMA
-  uint64_t* pload = aempty + 2;           // [4] TMA load of the previous pass's partial sums -> epilogue warp
+  uint64_t* pload = aempty + 2;           // [4][2] TMA load of the previous pass's partial sums -> epilogue warp, per staging set
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + G_NBAR);
 
   const int warp = threadIdx.x >> 5;
@@ -245,7 +251,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
     tma_prefetch_desc(&map_out_hi);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < G_NS; ++s) {
+    for (int s = 0; s < NS; ++s) {
       mbar_init(&ofull[s], 1);
       mbar_init(&oempty[s], 1);
     }
@@ -260,7 +266,8 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
     for (int s = 0; s < 4; ++s) {
       mbar_init(&qfull[s], 128);
       mbar_init(&qempty[s], 1);
-      mbar_init(&pload[s], 1);
+      mbar_init(&pload[2 * s], 1);
+      mbar_init(&pload[2 * s + 1], 1);
     }
     fence_barrier_init();
   }
@@ -298,7 +305,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
               tma_load_3d(&map_kwd, &ofull[stage], sa + G_A_BYTES, kb * 64, ROWS * n - 3, (p.c0 + c) * p.K + w.kw);
               KWS_TRACE(3, tr_stage, 3);  // loads issued
               ++tr_stage;
-              if (++stage == G_NS) stage = 0, phase ^= 1;
+              if (++stage == NS) stage = 0, phase ^= 1;
             }
           }
         }
@@ -337,7 +344,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
             umma_commit(&oempty[o_stage]);
             KWS_TRACE(3, tr_s, 5);
             ++tr_s;
-            if (++o_stage == G_NS) o_stage = 0, o_phase ^= 1;
+            if (++o_stage == NS) o_stage = 0, o_phase ^= 1;
             // layer pair complete (or last layer of an odd C): hand its tiles to the converters
             if (kb == p.nkb - 1 && ((c & 1) == 1 || c == p.C - 1)) umma_commit(&sfull[c >> 1]);
             if (st == stages_per_chunk - 1) KWS_TRACE(2, g, 5);
@@ -437,7 +444,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
     const int ojl = (q & 1) * 32 + lane;
     const bool lo_warp = (q & 1) == 0;
     constexpr bool nhwc = NHWC;
-    uint8_t* my_stage = s_ostage + q * (32 * 128);
+    uint8_t* const stage0 = s_ostage + q * (32 * 128);  // MULTI: set (step & 1) at + G_OUT_STAGE
     // mailboxes (2 lanes x 32 fp32 per channel group) live in the hi warp's never-stored pixel rows 28..31
     float* mbox0 = reinterpret_cast<float*>(s_ostage + (q | 1) * (32 * 128) + 28 * 128);
     float* mbox1 = mbox0 + 64;
@@ -456,7 +463,24 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
     uint32_t acc_seq = 0;
-    uint32_t pl_seq = 0;  // partial-sum tiles loaded so far by this warp (phase of pload[q])
+    uint32_t pl_seq[2] = {0u, 0u};  // partial-sum tiles consumed so far from each staging set (phase of pload[q][set])
+    // Partial sums of the previous channel-group pass: the tile of step n+1 is TMA-loaded into the other staging set
+    // while step n is processed (a load issued and awaited inside one step would put its whole latency, ~2 k cycles
+    // behind the tensor core's operand reads, on the epilogue's critical path).
+    auto load_prev = [&](uint32_t set, int ct, int oi, int pair) {
+      mbar_arrive_expect_tx(&pload[2 * q + set], (lo_warp ? 32u : (uint32_t)(G_TILE_OJ - 32)) * 128u);
+      asm volatile(
+          "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+          "%6}], [%2];" ::"r"(smem_u32(stage0 + set * G_OUT_STAGE)),
+          "l"(reinterpret_cast<uint64_t>(my_map)), "r"(smem_u32(&pload[2 * q + set])), "r"(0),
+          "r"(ct * G_TILE_OJ + (q & 1) * 32), "r"(oi), "r"(pair)
+          : "memory");
+    };
+    auto tile_ok_at = [&](int ct, int oi) { return oi < p.Ho && ct * G_TILE_OJ + (q & 1) * 32 < p.Wo; };
+    if (MULTI && nhwc && p.prefetch == 1 && p.acc_mode >= 2 && lane == 0 && (long long)blockIdx.x < p.num_items) {
+      const ItemCoord w0 = decode_item(p, blockIdx.x);
+      if (tile_ok_at(w0.ct, row_sel)) load_prev(0u, w0.ct, row_sel, (int)w0.pair);
+    }
     long long te_wait = 0, te_ld = 0, te_rest = 0;
     long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (long long it = blockIdx.x; it < p.num_items; it += gridDim.x) {
@@ -474,7 +498,9 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
         const uint32_t t_row = tmem_base + acc * G_ACC_COLS + ((uint32_t)(q * 32) << 16);
         const int oi = 2 * P + row_sel;
         const bool ok = col_ok && oi < p.Ho;
-        const bool tile_ok = oi < p.Ho && w.ct * G_TILE_OJ + (q & 1) * 32 < p.Wo;  // this warp stores a tile this step
+        const bool tile_ok = tile_ok_at(w.ct, oi);  // this warp stores a tile this step
+        const uint32_t set = (MULTI && p.prefetch == 1) ? (acc_seq & 1u) : 0u;
+        uint8_t* const my_stage = stage0 + set * G_OUT_STAGE;
         float* o32 = nullptr;
         long long oc_stride = 0;
         if (!nhwc) {
@@ -482,45 +508,62 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
           oc_stride = (long long)p.Ho * p.Wo;
         }
         uint8_t* srow = my_stage + lane * 128;
+        // 32 output channels per TMEM round trip; 16 in the multi-pass instance, whose partial-sum registers would
+        // otherwise spill (with the L1 carved into shared memory a spill is an L2 round trip)
+        constexpr int NH = MULTI ? NHM : 2, NG = 4 / NH;
 #pragma unroll 1  // a real loop: the role loops are instruction-cache bound, not ILP bound
-        for (int grp = 0; grp < 2; ++grp) {  // 32 output channels per TMEM round trip
-          uint32_t va[2][16], vb[2][16], vbias[2][16];
+        for (int grp = 0; grp < NG; ++grp) {
+          uint32_t va[NH][16], vb[NH][16], vbias[NH][16];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            tmem_ld16(t_row + G_OC + grp * 32 + h * 16, vb[h]);
-            tmem_ld16(t_row + grp * 32 + h * 16, va[h]);
-            tmem_ld16(tmem_base + G_TMEM_BIAS + ((uint32_t)(q * 32) << 16) + grp * 32 + h * 16, vbias[h]);
+          for (int h = 0; h < NH; ++h) {
+            tmem_ld16(t_row + G_OC + grp * (16 * NH) + h * 16, vb[h]);
+            tmem_ld16(t_row + grp * (16 * NH) + h * 16, va[h]);
+            tmem_ld16(tmem_base + G_TMEM_BIAS + ((uint32_t)(q * 32) << 16) + grp * (16 * NH) + h * 16, vbias[h]);
           }
           if (grp == 0) {
             // the previous step's TMA store must have read this warp's staging buffer before it is reused
             if (lane == 0) {
               asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-              if (nhwc && MULTI && p.acc_mode >= 2 && tile_ok) {
-                // partial sums of the previous channel-group pass: same tile, same staging layout
-                mbar_arrive_expect_tx(&pload[q], (lo_warp ? 32u : (uint32_t)(G_TILE_OJ - 32)) * 128u);
-                asm volatile(
-                    "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
-                    "%6}], [%2];" ::"r"(smem_u32(my_stage)),
-                    "l"(reinterpret_cast<uint64_t>(my_map)), "r"(smem_u32(&pload[q])), "r"(0),
-                    "r"(w.ct * G_TILE_OJ + (q & 1) * 32), "r"(oi), "r"((int)w.pair)
-                    : "memory");
+              if (nhwc && MULTI && p.acc_mode >= 2 && p.prefetch != 1) {
+                if (tile_ok) load_prev(0u, w.ct, oi, (int)w.pair);  // awaited below, in this step
+                if (p.prefetch == 2) {  // next step's tile: HBM -> L2 now, so that its load is an L2 hit
+                  int nct = w.ct, noi = oi + 2, npair = (int)w.pair;
+                  bool have = P + 1 < p.nP;
+                  if (!have && it + gridDim.x < p.num_items) {
+                    const ItemCoord wn = decode_item(p, it + gridDim.x);
+                    nct = wn.ct, noi = row_sel, npair = (int)wn.pair, have = true;
+                  }
+                  if (have && tile_ok_at(nct, noi))
+                    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(
+                                     reinterpret_cast<uint64_t>(my_map)),
+                                 "r"(0), "r"(nct * G_TILE_OJ + (q & 1) * 32), "r"(noi), "r"(npair)
+                                 : "memory");
+                }
+              } else if (nhwc && MULTI && p.acc_mode >= 2) {
+                // the other staging set is free now (its store has been read): prefetch the next step's partial sums
+                if (P + 1 < p.nP) {
+                  if (tile_ok_at(w.ct, oi + 2)) load_prev(set ^ 1u, w.ct, oi + 2, (int)w.pair);
+                } else if (it + gridDim.x < p.num_items) {
+                  const ItemCoord wn = decode_item(p, it + gridDim.x);
+                  if (tile_ok_at(wn.ct, row_sel)) load_prev(set ^ 1u, wn.ct, row_sel, (int)wn.pair);
+                }
               }
             }
             __syncwarp();
           }
           tmem_ld_wait();
           const long long f0 = KWS_CLK();
-          if (grp == 1) {  // last TMEM read of this accumulator
+          if (grp == NG - 1) {  // last TMEM read of this accumulator
             tc_fence_before();
             mbar_arrive(&aempty[acc]);
             if (warp == 4 && lane == 0) KWS_TRACE(1, acc_seq, 1);
             te_ld += KWS_CLK() - e1;
           }
-          float* mbox = grp == 0 ? mbox0 : mbox1;
+          float* mbox = (grp & 1) == 0 ? mbox0 : mbox1;
           if (!lo_warp && lane < 2) {
             float4* dst = reinterpret_cast<float4*>(mbox + lane * 32);
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
+            for (int h = 0; h < NH; ++h)
 #pragma unroll
               for (int e = 0; e < 16; e += 4)
                 dst[h * 4 + (e >> 2)] = make_float4(__uint_as_float(vb[h][e]), __uint_as_float(vb[h][e + 1]),
@@ -529,13 +572,13 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
           named_bar_sync(1 + row_sel, 64);  // mailbox written (and the other mailbox has been read)
           const long long f1 = KWS_CLK();
 #pragma unroll
-          for (int h = 0; h < 2; ++h)
+          for (int h = 0; h < NH; ++h)
 #pragma unroll
             for (int e = 0; e < 16; ++e) vb[h][e] = __shfl_down_sync(0xffffffffu, vb[h][e], 2);
           if (lo_warp && lane >= 30) {
             const float4* src = reinterpret_cast<const float4*>(mbox + (lane - 30) * 32);
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
+            for (int h = 0; h < NH; ++h)
 #pragma unroll
               for (int e = 0; e < 16; e += 4) {
                 const float4 f = src[h * 4 + (e >> 2)];
@@ -544,8 +587,8 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
               }
           }
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int ch = grp * 2 + h;
+          for (int h = 0; h < NH; ++h) {
+            const int ch = grp * NH + h;
             if constexpr (nhwc) {
               const bool with_bias = !MULTI || p.acc_mode == 0 || p.acc_mode == 3;  // single or last channel-group pass
               const bool add_prev = MULTI && p.acc_mode >= 2 && tile_ok;
@@ -553,7 +596,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
               uint8_t* c1p = srow + (((2 * ch + 1) ^ (lane & 7)) << 4);
               uint32_t prev[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
               if (add_prev) {  // fp16 partial sums of the previous passes, TMA-loaded into the staging tile
-                if (grp == 0 && h == 0) mbar_wait(&pload[q], pl_seq & 1, 950 + q);
+                if (grp == 0 && h == 0) mbar_wait(&pload[2 * q + set], pl_seq[set] & 1, 950 + q);
                 const uint4 a = *reinterpret_cast<const uint4*>(c0p), b = *reinterpret_cast<const uint4*>(c1p);
                 prev[0] = a.x, prev[1] = a.y, prev[2] = a.z, prev[3] = a.w;
                 prev[4] = b.x, prev[5] = b.y, prev[6] = b.z, prev[7] = b.w;
@@ -596,13 +639,13 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
             }
           }
           const long long f2 = KWS_CLK();
-          tp[grp * 3 + 0] += f0 - (grp == 0 ? e1 : tp[7]);
-          tp[grp * 3 + 1] += f1 - f0;
-          tp[grp * 3 + 2] += f2 - f1;
+          tp[(grp & 1) * 3 + 0] += f0 - (grp == 0 ? e1 : tp[7]);
+          tp[(grp & 1) * 3 + 1] += f1 - f0;
+          tp[(grp & 1) * 3 + 2] += f2 - f1;
           tp[7] = f2;
         }
         if constexpr (nhwc) {
-          if (MULTI && p.acc_mode >= 2 && tile_ok) ++pl_seq;
+          if (MULTI && p.acc_mode >= 2 && tile_ok) ++pl_seq[set];
           fence_proxy_async();
           __syncwarp();
           if (lane == 0 && tile_ok) {
@@ -741,11 +784,12 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
   }
 }
 
-constexpr size_t g_smem_bytes(int rows, int n_mma) {
-  return (size_t)G_NS * g_stage_bytes(rows) + (size_t)7 * n_mma * G_MMA_W_BYTES + G_OUT_STAGE + G_RING_BYTES - 64 +
-         G_NBAR * 8 + 16;
+constexpr size_t g_smem_bytes(int rows, int n_mma, bool two_sets = false) {
+  return (size_t)G_NS * g_stage_bytes(rows) + (size_t)7 * n_mma * G_MMA_W_BYTES +
+         (two_sets ? 2 : 1) * G_OUT_STAGE + G_RING_BYTES - 64 + G_NBAR * 8 + 16;
 }
-static_assert(g_smem_bytes(16, 3) <= 232448 && g_smem_bytes(32, 2) <= 232448 && g_smem_bytes(48, 2) <= 232448,
+static_assert(g_smem_bytes(16, 3) <= 232448 && g_smem_bytes(32, 2) <= 232448 && g_smem_bytes(48, 2) <= 232448 &&
+                  g_smem_bytes(16, 2, true) <= 232448,
               "fused kernel exceeds the 227 KB shared-memory limit");
 
 // Fused-kernel weight layout: [di 7][m n_mma][chunk 2][n 128][e 8] fp16, BN scale folded.
@@ -796,11 +840,38 @@ extern "C" void kws_debug_set_fused_grid_limit(int n) { g_fused_grid_limit = n; 
 extern "C" void kws_debug_set_fused_counters(long long* dev_buf) { g_fused_dbg = dev_buf; }
 
 static int fused_n_mma(int C) { return C <= 8 ? 2 : 3; }
-// C > 12 layers are processed in passes over channel groups of at most G_MAX_C layers; the passes chain their
+// C > 12 layers are processed in passes over channel groups of 12 layers; the passes chain their
 // partial sums through the output buffer itself (fp16, same tiles), the last one adds bias + ReLU -> bf16.
 constexpr int G_MAX_C_TOTAL = 64;
-static int fused_groups(int C) { return (C + G_MAX_C - 1) / G_MAX_C; }
-static int fused_group_layers(int C, int g) { return g < fused_groups(C) - 1 ? G_MAX_C : C - g * G_MAX_C; }
+static int g_multi_group = 12, g_multi_nh = 2, g_multi_prefetch = 2;
+// Multi-pass variants (development aid; measured at the cfg3 slab, pairs/s): layers per pass 12 | 8, output
+// channels / 16 per epilogue TMEM round trip 2 | 1, partial-sum prefetch 0 none | 1 into a second staging set
+// (8-layer groups only: their smaller weights leave the 16 KB free) | 2 into L2 only.
+//   12,2,2: 185 k (default)   12,2,0: 178 k   12,1,0: 162 k   8,2,1: 157 k   8,2,2: 149 k   8,1,1: 143 k   8,2,0: 135 k
+// The multi-pass epilogue (TMA load + add of the previous partial sums) is what bounds these shapes: the stem issuer
+// waits for accumulators, so fewer, fatter passes win even though the 2-trip epilogue spills 8 registers.
+extern "C" void kws_debug_set_fused_multi(int group, int nh, int prefetch) {
+  g_multi_group = group == 12 ? 12 : 8;
+  g_multi_nh = nh == 2 ? 2 : 1;
+  g_multi_prefetch = prefetch == 2 ? 2 : ((prefetch == 1 && g_multi_group == 8) ? 1 : 0);
+}
+static void multi_cfg_from_env() {  // development aid: KWS_FUSED_MULTI="group,nh,prefetch", read once
+  static bool done = false;
+  if (done) return;
+  done = true;
+  if (const char* e = getenv("KWS_FUSED_MULTI")) {
+    int g = 8, nh = 1, pf = 1;
+    if (sscanf(e, "%d,%d,%d", &g, &nh, &pf) == 3) kws_debug_set_fused_multi(g, nh, pf);
+  }
+}
+static int fused_group_size(int C) {
+  multi_cfg_from_env();
+  return C <= G_MAX_C ? G_MAX_C : g_multi_group;
+}
+static int fused_groups(int C) { return (C + fused_group_size(C) - 1) / fused_group_size(C); }
+static int fused_group_layers(int C, int g) {
+  return g < fused_groups(C) - 1 ? fused_group_size(C) : C - g * fused_group_size(C);
+}
 static size_t fused_group_bytes(int Cg) { return (size_t)7 * fused_n_mma(Cg) * G_MMA_W_BYTES; }
 
 extern "C" size_t kws_stem_fused_weight_bytes(int C) {
@@ -817,7 +888,7 @@ extern "C" int kws_pack_stem_fused(const float* conv_w, const float* gamma, cons
   uint8_t* dst = reinterpret_cast<uint8_t*>(w_fused);
   for (int g = 0; g < fused_groups(C); ++g) {
     const int Cg = fused_group_layers(C, g);
-    pack_stem_fused_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(conv_w, gamma, beta, mean, var, eps, C, g * G_MAX_C, Cg,
+    pack_stem_fused_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(conv_w, gamma, beta, mean, var, eps, C, g * fused_group_size(C), Cg,
                                                                  fused_n_mma(Cg), (__half*)dst, bias);
     KWS_CUDA(cudaGetLastError());
     dst += fused_group_bytes(Cg);
@@ -908,7 +979,7 @@ extern "C" int kws_sim_stem_range(const void* kwd_n, const void* utt_n, int C, i
     const int Cg = fused_group_layers(C, g);
     p.w = reinterpret_cast<const uint4*>(wsrc);
     p.C = Cg;
-    p.c0 = g * G_MAX_C;
+    p.c0 = g * fused_group_size(C);
     p.n_mma = fused_n_mma(Cg);
     p.acc_mode = n_groups == 1 ? 0 : (g == 0 ? 1 : (g == n_groups - 1 ? 3 : 2));
     p.w_bytes = (int)fused_group_bytes(Cg);
@@ -927,14 +998,15 @@ extern "C" int kws_sim_stem_range(const void* kwd_n, const void* utt_n, int C, i
     const bool nh = out_mode == KWS_STEM_OUT_NHWC_BF16;
     void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, FusedParams);
     if (p.acc_mode != 0) {
-      kern = kws_fused_kernel<true, 16, true>;  // groups of 12 (or the last 1..12) layers: 16-row chunks, bf16
-      KWS_CHECK_ARG(rows == 16 && nh, "sim_stem: internal: multi-pass needs 16-row chunks and bf16 output");
+      kern = g_multi_nh == 1 ? kws_fused_kernel<true, 16, true, 1> : kws_fused_kernel<true, 16, true, 2>;
+      p.prefetch = g_multi_prefetch;
+      KWS_CHECK_ARG(rows == 16 && nh, "sim_stem: internal: multi-pass needs 16-row chunks, bf16 output");
     } else {
       kern = rows == 48 ? (nh ? kws_fused_kernel<true, 48, false> : kws_fused_kernel<false, 48, false>)
              : rows == 32 ? (nh ? kws_fused_kernel<true, 32, false> : kws_fused_kernel<false, 32, false>)
                           : (nh ? kws_fused_kernel<true, 16, false> : kws_fused_kernel<false, 16, false>);
     }
-    const size_t smem = g_smem_bytes(rows, p.n_mma);
+    const size_t smem = g_smem_bytes(rows, p.n_mma, p.acc_mode != 0 && p.prefetch == 1);
     KWS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(int)grid, G_THREADS, smem, (cudaStream_t)stream>>>(mu, mk, mo_lo, mo_hi, p);
     KWS_CUDA(cudaGetLastError());

@@ -379,22 +379,32 @@ def test_cbw_keyword_spotter_logits_and_detections(built_lib, cuda_dev):
         assert det == [torch.nonzero(exp_hit[:, s]).flatten().tolist() for s in range(S)]
 
 
-@pytest.mark.parametrize("Cc,K,U,Tk,Tu", [(32, 2, 2, 75, 300), (16, 1, 2, 22, 130), (25, 2, 1, 9, 61)])
-def test_sim_stem_fused_channel_groups(ops, cuda_dev, Cc, K, U, Tk, Tu):
-    """More than 12 layers: one fused pass per group of 12 layers, fp16 partial sums chained through the output
-    buffer, bf16 channels-last result == conv2d on the fp16 similarity images (cfg3/cfg5 shape: C = 32)."""
-    g = gen(cuda_dev)
-    kn = unit_rows(Cc, K, Tk, 64, g=g, dev=cuda_dev).half()
-    un = unit_rows(Cc, U, Tu, 64, g=g, dev=cuda_dev).half()
-    kn[:, 0, Tk // 2:] = 0
-    sd = {k: v.to(cuda_dev) for k, v in O.make_weights("L", Cc, 64, seed=21).items()}
-    wf, bias = pack_stem_fused(ops, sd)
-    assert ops.sim_stem_supported(Cc, Tk, Tu, 64, ops.STEM_OUT_NHWC_BF16)
-    assert not ops.sim_stem_supported(Cc, Tk, Tu, 64, ops.STEM_OUT_NCHW_F32)
-    _, f16 = ops.sim(kn, un, False, True)
-    exp = stem_expect(f16, Tu, sd)
-    out = ops.sim_stem(kn, un, wf, bias, ops.STEM_OUT_NHWC_BF16)
-    assert out.shape == exp.shape
-    assert maxerr(out, exp) <= 2e-2 * max(1.0, exp.abs().max().item() / 4)
-    with pytest.raises(Exception):
-        ops.sim_stem(kn, un, wf, bias, ops.STEM_OUT_NCHW_F32)
+@pytest.mark.parametrize("multi", [(12, 2, 2), (12, 2, 0), (8, 1, 1), (8, 2, 1), (12, 1, 2)])
+@pytest.mark.parametrize("Cc,K,U,Tk,Tu", [(32, 2, 2, 75, 300), (16, 1, 2, 22, 130), (25, 2, 1, 9, 61), (13, 3, 50, 9, 130)])
+def test_sim_stem_fused_channel_groups(ops, cuda_dev, Cc, K, U, Tk, Tu, multi):
+    """More than 12 layers: one fused pass per group of layers, fp16 partial sums chained through the output
+    buffer, bf16 channels-last result == conv2d on the fp16 similarity images (cfg3/cfg5 shape: C = 32).
+    ``multi`` = (layers per pass, channels/16 per epilogue round trip, partial-sum prefetch: 0 none | 1 second
+    staging set | 2 L2 only); (12, 2, 2) is the shipped default, the others are the development variants."""
+    from enhance_cb_whisper_b200 import _lib
+
+    lib = _lib.load()
+    lib.kws_debug_set_fused_multi(*multi)
+    try:
+        g = gen(cuda_dev)
+        kn = unit_rows(Cc, K, Tk, 64, g=g, dev=cuda_dev).half()
+        un = unit_rows(Cc, U, Tu, 64, g=g, dev=cuda_dev).half()
+        kn[:, 0, Tk // 2:] = 0
+        sd = {k: v.to(cuda_dev) for k, v in O.make_weights("L", Cc, 64, seed=21).items()}
+        wf, bias = pack_stem_fused(ops, sd)  # packed per group: after the variant is chosen
+        assert ops.sim_stem_supported(Cc, Tk, Tu, 64, ops.STEM_OUT_NHWC_BF16)
+        assert not ops.sim_stem_supported(Cc, Tk, Tu, 64, ops.STEM_OUT_NCHW_F32)
+        _, f16 = ops.sim(kn, un, False, True)
+        exp = stem_expect(f16, Tu, sd)
+        out = ops.sim_stem(kn, un, wf, bias, ops.STEM_OUT_NHWC_BF16)
+        assert out.shape == exp.shape
+        assert maxerr(out, exp) <= 2e-2 * max(1.0, exp.abs().max().item() / 4)
+        with pytest.raises(Exception):
+            ops.sim_stem(kn, un, wf, bias, ops.STEM_OUT_NCHW_F32)
+    finally:
+        lib.kws_debug_set_fused_multi(12, 2, 2)

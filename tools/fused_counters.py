@@ -6,16 +6,16 @@ from enhance_cb_whisper_b200 import ops, _lib
 
 dev = torch.device("cuda:0")
 g = torch.Generator(device=dev).manual_seed(7)
-Cc, K, U, Tk, Tu, P = 12, 74, 2, 150, 1500, 64
+# usage: fused_counters.py [C Tk Tu K U]   (default: the cfg2 shape; C > 12 reports the LAST channel-group pass)
+Cc, Tk, Tu, K, U = (int(a) for a in sys.argv[1:6]) if len(sys.argv) >= 6 else (12, 150, 1500, 74, 2)
+P = 64
+Ho, Wo = (Tk + 1) // 2, (Tu + 1) // 2
 unit = lambda *s: torch.nn.functional.normalize(torch.randn(*s, generator=g, device=dev), dim=-1)
 kn, un = unit(Cc, K, Tk, P).half(), unit(Cc, U, Tu, P).half()
 wp, bias = ops.pack_stem_fused(torch.randn(64, Cc, 7, 7, generator=g, device=dev) * 0.05, torch.ones(64, device=dev),
                                  torch.zeros(64, device=dev), torch.zeros(64, device=dev), torch.ones(64, device=dev))
-out = torch.empty(K * U, 75, 750, 64, dtype=torch.bfloat16, device=dev)
+out = torch.empty(K * U, Ho, Wo, 64, dtype=torch.bfloat16, device=dev)
 ops.sim_stem(kn, un, wp, bias, ops.STEM_OUT_NHWC_BF16, out=out)
-if len(sys.argv) > 1:
-    _lib.load().kws_debug_set_fused_skip(int(sys.argv[1]))
-    print("dbg_skip", sys.argv[1])
 buf = torch.zeros(148, 32, dtype=torch.int64, device=dev)
 lib = _lib.load()
 lib.kws_debug_set_fused_counters.argtypes = [ctypes.c_void_p]
@@ -24,7 +24,9 @@ ops.sim_stem(kn, un, wp, bias, ops.STEM_OUT_NHWC_BF16, out=out)
 torch.cuda.synchronize()
 lib.kws_debug_set_fused_counters(None)
 b = buf.double().mean(0).tolist()
-items = K * U * 13 / 148
+items = K * U * ((Wo + 59) // 60) / 148
+steps = (Ho + 1) // 2
+print(f"C={Cc} {Tk}x{Tu} K={K} U={U}: {steps} steps/item")
 print(f"per item (mean over CTAs, {items:.1f} items/CTA): total {b[0]/items:.0f} cyc | deadline-sim wait {b[1]/items:.0f} | "
       f"aempty wait {b[2]/items:.0f} | qfull wait {b[3]/items:.0f} | issue {b[4]/items:.0f}")
 print(f"  epilogue: afull wait {b[5]/items:.0f} | until acc released {b[6]/items:.0f} | whole step body {b[7]/items:.0f}")
