@@ -17,7 +17,7 @@ ABI_VERSION = 6
 # constants of include/kws_b200.h
 F16, BF16 = 0, 1
 MLP_OUT_NORM_F16, MLP_OUT_RAW_F32, MLP_OUT_RAW_16 = 0, 1, 2
-PAIRS_ALL, PAIRS_DIAG = 0, 1
+PAIRS_ALL, PAIRS_DIAG, PAIRS_PER_KEYWORD = 0, 1, 2
 STEM_OUT_NCHW_F32, STEM_OUT_NHWC_BF16 = 0, 1
 
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
@@ -44,6 +44,9 @@ SIGNATURES = {
     "kws_sim_stem_supported": (_i, [_i, _i, _i, _i]),
     "kws_sim_stem_range": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "kws_resize_bilinear": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "kws_interp_rows": (_i, [_vp, _i, _i, _i, _i, C.POINTER(C.c_int32), _i, _i, _f, _vp, _vp]),
+    "kws_sim_operand": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "kws_resize_row_weights": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "kws_maxpool_nhwc": (_i, [_vp, C.c_longlong, _i, _i, _i, _vp, _vp]),
     "kws_scores": (_i, [_vp, _vp, _sz, _f, _vp, _vp, _vp]),
     "kws_topk": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),

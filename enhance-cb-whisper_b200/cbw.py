@@ -11,10 +11,20 @@ Mirrors the two reference pieces that make up this variant of the hot path:
   (ResNet stem + body + head) and the ``argmax(logits) == 1`` detection rule of
   src/model/cb_whisper.py:128.
 
-Here the ragged keywords are zero-padded into one resident fp16 bank, all keyword x segment
-similarities run through the tcgen05 GEMM (``kws_sim``), one resize kernel produces the fp16
-classifier input (``kws_resize_bilinear``) and the stem runs in ``kws_stem``; the ResNet body and
-head are the unmodified HuggingFace / torch modules.  CUDA only, inference only.
+Here the ragged keywords are zero-padded into one resident fp16 bank.  Two paths:
+
+* ``similarity_images`` (parity with the reference's intermediate): all keyword x segment similarities through
+  the tcgen05 GEMM (``kws_sim``), one resize kernel (``kws_resize_bilinear``) -> the [K,S,C,150,750] images.
+* ``CBWKeywordSpotterB200.logits`` (the scoring path): the resized image is never built.  Bilinear resize is
+  linear and separable and the similarity is bilinear in its operands, so
+  ``resize(kwd . utt^T) = (Wy kwd) . (Wx utt)^T``: the width map is applied to the utterance frames
+  (``kws_interp_rows``: 1500 -> 750 frames halves the GEMM), the native-resolution similarity is written as a
+  64-wide fp16 operand (``kws_sim_operand``), the height map is an operand of its own
+  (``kws_resize_row_weights``), and the fused similarity+stem kernel (``kws_sim_stem``, Dk = 64,
+  ``KWS_PAIRS_PER_KEYWORD``) contracts the two and applies the stem.  Keywords longer than 64 frames fall back to
+  images + ``kws_stem``.
+
+The ResNet body and head are library code (``body.py`` / the unmodified modules).  CUDA only, inference only.
 """
 from __future__ import annotations
 
@@ -23,7 +33,10 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import ops
+from .body import FusedBody
 from .model import run_body
+
+FUSED_MAX_FRAMES = 64  # keyword frames the fused path holds as the contraction dimension of the height map
 
 
 def pack_keywords(kwd_list: Sequence[torch.Tensor], device: torch.device, multiple: int = 16):
@@ -88,6 +101,7 @@ class CBWKeywordSpotterB200:
         self.size = tuple(size)
         self.body_dtype = body_dtype
         self._packed = None
+        self._packed_fused = None
         self._lowp = None
 
     def _weights(self, device):
@@ -99,31 +113,80 @@ class CBWKeywordSpotterB200:
                                                  emb.normalization.running_var.to(device))
         return self._packed
 
+    def _weights_fused(self, device):
+        if self._packed_fused is None or self._packed_fused[0].device != device:
+            emb = self.resnet.feature_extractor.embedder.embedder
+            self._packed_fused = ops.pack_stem_fused(emb.convolution.weight.to(device), emb.normalization.weight.to(device),
+                                                     emb.normalization.bias.to(device),
+                                                     emb.normalization.running_mean.to(device),
+                                                     emb.normalization.running_var.to(device))
+        return self._packed_fused
+
     def _body(self, st):
         if self.body_dtype == "float32":
             return run_body(self.resnet, st)
-        if self._lowp is None:
-            import copy
-
-            m = copy.deepcopy(self.resnet).to(dtype=torch.bfloat16, memory_format=torch.channels_last)
-            m.classifier.float()
-            self._lowp = m.eval()
-        return run_body(self._lowp, st)
+        if self._lowp is None:  # BatchNorms folded + cuDNN fused convolutions (body.py), max-pool in libkws_b200
+            self._lowp = FusedBody(self.resnet, torch.bfloat16)
+        return self._lowp(ops.maxpool_nhwc(st), pooled=True)
 
     @torch.no_grad()
-    def logits(self, kwd_list: Sequence[torch.Tensor], utt_hs: torch.Tensor, max_pairs: int = 128) -> torch.Tensor:
-        """-> logits fp32 [K, S, 2] for every keyword x segment."""
+    def stem_fused(self, kwd_n: torch.Tensor, lens: torch.Tensor, utt_i: torch.Tensor, out_mode: int,
+                   max_pairs: int = 256, consume=None):
+        """Scoring path up to the stem activation, resized image never built.  kwd_n fp16 [C,K,64,D] (pack_keywords),
+        lens int32 [K], utt_i fp16 [C,S,Wi,D] (ops.interp_rows to the image width).  Calls
+        ``consume(k0, k1, stem_activation [(k1-k0)*S, 64, Ho, Wo])`` per block of keywords."""
+        C, K, Tkp, _ = kwd_n.shape
+        S = utt_i.shape[1]
+        wf, bias = self._weights_fused(kwd_n.device)
+        kb = max(1, min(K, max_pairs // max(S, 1)))
+        for k0 in range(0, K, kb):
+            k1 = min(K, k0 + kb)
+            s_op = ops.sim_operand(kwd_n[:, k0:k1].contiguous() if (k0, k1) != (0, K) else kwd_n, utt_i)
+            wy = ops.resize_row_weights(lens[k0:k1].contiguous(), k1 - k0, C, Tkp, self.size[0])
+            st = ops.sim_stem(wy, s_op, wf, bias, out_mode, per_keyword=True)
+            if consume is not None:
+                consume(k0, k1, st)
+
+    def fused_ok(self, kwd_list, utt_hs) -> bool:
+        C = utt_hs.shape[1]
+        return (max(int(k.shape[1]) for k in kwd_list) <= FUSED_MAX_FRAMES and utt_hs.shape[3] % 64 == 0
+                and utt_hs.shape[3] <= 1280 and bool(ops.sim_stem_supported(C, self.size[0], self.size[1], 64,
+                                                                            ops.STEM_OUT_NHWC_BF16 if self.body_dtype != "float32"
+                                                                            else ops.STEM_OUT_NCHW_F32)))
+
+    @torch.no_grad()
+    def logits(self, kwd_list: Sequence[torch.Tensor], utt_hs: torch.Tensor, max_pairs: int = 128,
+               fused: Optional[bool] = None) -> torch.Tensor:
+        """-> logits fp32 [K, S, 2] for every keyword x segment.  ``fused``: None = use the fused path when the
+        shapes allow (keywords <= 64 frames), False = images + un-fused stem, True = insist."""
         dev = utt_hs.device
+        if not utt_hs.is_cuda:
+            raise ops.KWSError("utt_hs must be a CUDA tensor (the kws_b200 path has no CPU fallback)")
+        lowp = self.body_dtype != "float32"
+        out_mode = ops.STEM_OUT_NHWC_BF16 if lowp else ops.STEM_OUT_NCHW_F32
+        use_fused = self.fused_ok(kwd_list, utt_hs) if fused is None else fused
+        if use_fused:
+            if not self.fused_ok(kwd_list, utt_hs):
+                raise ops.KWSError("fused config-#4 path needs keywords <= 64 frames, D % 64 == 0, D <= 1280")
+            S, C = utt_hs.shape[0], utt_hs.shape[1]
+            kwd_n, lens = pack_keywords(kwd_list, dev, multiple=FUSED_MAX_FRAMES)
+            utt_i = ops.interp_rows(utt_hs.float().contiguous(), list(range(C)), self.size[1])
+            K = kwd_n.shape[1]
+            out = torch.empty((K, S, 2), dtype=torch.float32, device=dev)
+
+            def consume(k0, k1, st):
+                out[k0:k1] = self._body(st).float().view(k1 - k0, S, 2)
+
+            self.stem_fused(kwd_n, lens, utt_i, out_mode, max_pairs, consume)
+            return out
         _, f16 = similarity_images(kwd_list, utt_hs, self.size, want_f32=False, want_f16=True)
         K, S = f16.shape[:2]
         wp, bias = self._weights(dev)
-        lowp = self.body_dtype != "float32"
         flat = f16.view(K * S, *f16.shape[2:])
         out = torch.empty((K * S, 2), dtype=torch.float32, device=dev)
         for p0 in range(0, K * S, max_pairs):
             p1 = min(K * S, p0 + max_pairs)
-            st = ops.stem(flat[p0:p1], self.size[1], wp, bias,
-                          ops.STEM_OUT_NHWC_BF16 if lowp else ops.STEM_OUT_NCHW_F32)
+            st = ops.stem(flat[p0:p1], self.size[1], wp, bias, out_mode)
             out[p0:p1] = self._body(st).float()
         return out.view(K, S, 2)
 

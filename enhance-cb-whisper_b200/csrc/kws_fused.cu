@@ -117,6 +117,7 @@ struct FusedParams {
   int n_chunks;  // similarity chunks (ROWS input rows = ROWS/4 quanta) per item
   int w_bytes;   // bytes of this pass's stem weights in shared memory (7 * n_mma * 4096)
   int diag;
+  int per_kw_u;  // KWS_PAIRS_PER_KEYWORD: utterance-side operand of pair (k, u) is bank item k * per_kw_u + u (else 0)
   int prefetch;  // multi-pass partial sums of step n+1: 1 = loaded into a second staging set during step n;
                  // 2 = pulled into L2 only (TMA prefetch), loaded and awaited in step n+1; 0 = neither
   long long num_items;
@@ -193,6 +194,7 @@ __device__ __forceinline__ ItemCoord decode_item(const FusedParams& p, long long
     const int kl = (int)(r.pair / p.nu);
     r.kw = p.k0 + kl;
     r.u = p.u0 + (int)(r.pair - (long long)kl * p.nu);
+    if (p.per_kw_u) r.u += r.kw * p.per_kw_u;
   }
   return r;
 }
@@ -481,7 +483,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
       const ItemCoord w0 = decode_item(p, blockIdx.x);
       if (tile_ok_at(w0.ct, row_sel)) load_prev(0u, w0.ct, row_sel, (int)w0.pair);
     }
-    long long te_wait = 0, te_ld = 0, te_rest = 0;
+    long long te_wait = 0, te_ld = 0, te_rest = 0, te_pl = 0, te_lds = 0;
     long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (long long it = blockIdx.x; it < p.num_items; it += gridDim.x) {
       const ItemCoord w = decode_item(p, it);
@@ -596,10 +598,16 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
               uint8_t* c1p = srow + (((2 * ch + 1) ^ (lane & 7)) << 4);
               uint32_t prev[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
               if (add_prev) {  // fp16 partial sums of the previous passes, TMA-loaded into the staging tile
+                const long long g0 = KWS_CLK();
                 if (grp == 0 && h == 0) mbar_wait(&pload[2 * q + set], pl_seq[set] & 1, 950 + q);
+                const long long g1 = KWS_CLK();
                 const uint4 a = *reinterpret_cast<const uint4*>(c0p), b = *reinterpret_cast<const uint4*>(c1p);
                 prev[0] = a.x, prev[1] = a.y, prev[2] = a.z, prev[3] = a.w;
                 prev[4] = b.x, prev[5] = b.y, prev[6] = b.z, prev[7] = b.w;
+#ifdef KWS_FUSED_TIMERS
+                asm volatile("" ::"r"(prev[0]), "r"(prev[7]));  // the loads have landed before the clock is read
+                te_pl += g1 - g0, te_lds += KWS_CLK() - g1;
+#endif
               }
               uint32_t o[8];
 #pragma unroll
@@ -665,7 +673,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all stores complete before exit
     if (p.dbg && warp == 4 && lane == 0) {
       long long* o = p.dbg + (size_t)blockIdx.x * 32;
-      o[5] = te_wait, o[6] = te_ld, o[7] = te_rest;
+      o[5] = te_wait, o[6] = te_ld, o[7] = te_rest, o[12] = te_pl, o[13] = te_lds;
       for (int i = 0; i < 7; ++i) o[16 + i] = tp[i];
     }
   } else if (warp >= 8) {
@@ -920,16 +928,21 @@ extern "C" int kws_sim_stem_range(const void* kwd_n, const void* utt_n, int C, i
   KWS_CHECK_ARG(C <= G_MAX_C || out_mode == KWS_STEM_OUT_NHWC_BF16,
                 "sim_stem: C=%d > %d layers needs the bf16 channels-last output (multi-pass partial sums)", C, G_MAX_C);
   KWS_CHECK_ARG(Dk % 64 == 0 && Dk >= 64, "sim_stem: Dk=%d must be a multiple of 64", Dk);
-  KWS_CHECK_ARG(pair_mode == KWS_PAIRS_ALL || pair_mode == KWS_PAIRS_DIAG, "sim_stem: bad pair_mode %d", pair_mode);
-  KWS_CHECK_ARG(pair_mode == KWS_PAIRS_ALL || (U == K && k0 == u0 && nk == nu),
+  KWS_CHECK_ARG(pair_mode == KWS_PAIRS_ALL || pair_mode == KWS_PAIRS_DIAG || pair_mode == KWS_PAIRS_PER_KEYWORD,
+                "sim_stem: bad pair_mode %d", pair_mode);
+  KWS_CHECK_ARG(pair_mode != KWS_PAIRS_DIAG || (U == K && k0 == u0 && nk == nu),
                 "sim_stem: KWS_PAIRS_DIAG needs U == K and equal ranges (got K=%d U=%d)", K, U);
+  KWS_CHECK_ARG(pair_mode != KWS_PAIRS_PER_KEYWORD || (long long)K * U < (1ll << 31) / (C > 0 ? C : 1),
+                "sim_stem: KWS_PAIRS_PER_KEYWORD bank of K*U=%lld items too large", (long long)K * U);
   KWS_CHECK_ARG(out_mode == KWS_STEM_OUT_NCHW_F32 || out_mode == KWS_STEM_OUT_NHWC_BF16, "sim_stem: bad out_mode %d",
                 out_mode);
   KWS_CHECK_ARG((reinterpret_cast<uintptr_t>(w_fused) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                 "sim_stem: pointers must be 16-byte aligned");
   CUtensorMap mu;
   {
-    const uint64_t dims[3] = {(uint64_t)Dk, (uint64_t)Tu, (uint64_t)C * U};
+    // KWS_PAIRS_PER_KEYWORD: the utterance-side bank holds one item per (keyword, utterance)
+    const uint64_t u_bank = pair_mode == KWS_PAIRS_PER_KEYWORD ? (uint64_t)K * U : (uint64_t)U;
+    const uint64_t dims[3] = {(uint64_t)Dk, (uint64_t)Tu, (uint64_t)C * u_bank};
     const uint64_t strides[2] = {(uint64_t)Dk * 2, (uint64_t)Dk * 2 * (uint64_t)Tu};
     const uint32_t box[3] = {64, 128, 1};
     if (int e = make_tensor_map(&mu, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, utt_n, dims, strides, box,
@@ -957,7 +970,8 @@ extern "C" int kws_sim_stem_range(const void* kwd_n, const void* utt_n, int C, i
   p.bias = bias;
   p.out = out;
   p.out_mode = out_mode;
-  p.K = K, p.U = U, p.Tk = Tk, p.Tu = Tu, p.nkb = Dk / 64;
+  p.K = K, p.U = pair_mode == KWS_PAIRS_PER_KEYWORD ? K * U : U, p.Tk = Tk, p.Tu = Tu, p.nkb = Dk / 64;
+  p.per_kw_u = pair_mode == KWS_PAIRS_PER_KEYWORD ? U : 0;
   p.k0 = k0, p.u0 = u0, p.nk = nk, p.nu = nu;
   p.C_total = C;
   p.Ho = Ho;

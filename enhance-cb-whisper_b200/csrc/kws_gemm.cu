@@ -52,6 +52,7 @@ struct GemmParams {
   float eps;
   // SIM
   int K, U, C, Tk, Tu, pitch16, diag;
+  int operand_out;  // SIM: out2 = fp16 [C, pairs, Tu, block_n] (the accumulator tile as it is: a K-major operand)
 };
 
 struct Item {
@@ -189,7 +190,24 @@ kws_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const int n_chunks = p.block_n >> 4;
       uint32_t v[16];
 
-      if (p.epi == EPI_SIM) {
+      if (p.epi == EPI_SIM && p.operand_out) {
+        // the tile as a K-major fp16 operand of a following GEMM: row = utterance frame, block_n keyword frames
+        // contiguous (config #4: contracted with the resize's height map inside the fused kernel)
+        const long long n_pairs = p.diag ? (long long)p.K : (long long)p.K * p.U;
+        __half* o = reinterpret_cast<__half*>(p.out2) + (((long long)w.c * n_pairs + w.pair) * p.Tu + row) * p.block_n;
+        for (int ch = 0; ch < n_chunks; ++ch) {
+          tmem_ld16(t_row + ch * 16, v);
+          tmem_ld_wait();
+          if (row_ok) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) pk[e] = pack_half2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+            uint4* dst = reinterpret_cast<uint4*>(o + ch * 16);
+            dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+        }
+      } else if (p.epi == EPI_SIM) {
         // row = utterance frame j, column = keyword frame i; out[pair][c][i][j]
         float* o32 = p.out ? reinterpret_cast<float*>(p.out) + ((w.pair * p.C + w.c) * p.Tk) * (long long)p.Tu + row
                            : nullptr;
@@ -458,6 +476,32 @@ int kws_sim(const void* kwd_n, const void* utt_n, int C, int K, int U, int Tk, i
   p.out = feat_f32;
   p.out2 = feat_f16;
   p.K = K, p.U = U, p.C = C, p.Tk = Tk, p.Tu = Tu, p.pitch16 = pitch16;
+  return launch_gemm(ma, mb, p, (cudaStream_t)stream);
+}
+
+int kws_sim_operand(const void* kwd_n, const void* utt_n, int C, int K, int U, int Tk, int Tu, int Dk, void* out_f16,
+                    void* stream) {
+  KWS_CHECK_ARG(kwd_n && utt_n && out_f16, "sim_operand: null pointer");
+  KWS_CHECK_ARG(C > 0 && K > 0 && U > 0 && Tk > 0 && Tu > 0, "sim_operand: non-positive dimension");
+  KWS_CHECK_ARG(Dk % 64 == 0 && Dk >= 64, "sim_operand: Dk=%d must be a multiple of 64", Dk);
+  KWS_CHECK_ARG(Tk % 16 == 0 && Tk <= 256, "sim_operand: Tk=%d must be a multiple of 16, <= 256 (zero-pad the bank)", Tk);
+  KWS_CHECK_ARG((reinterpret_cast<uintptr_t>(out_f16) & 15) == 0, "sim_operand: out must be 16-byte aligned");
+  CUtensorMap ma, mb;
+  if (int e = operand_map(&ma, utt_n, Dk, Tu, (long long)C * U, BLOCK_M)) return e;
+  if (int e = operand_map(&mb, kwd_n, Dk, Tk, (long long)C * K, Tk)) return e;
+  GemmParams p{};
+  p.epi = EPI_SIM;
+  p.operand_out = 1;
+  p.num_kblocks = Dk / BLOCK_K;
+  p.block_n = Tk;
+  p.idesc = make_idesc_f16(BLOCK_M, Tk, 0);
+  p.m_tiles = (Tu + BLOCK_M - 1) / BLOCK_M;
+  p.n_tiles = 1;
+  p.num_items = (long long)K * U * C * p.m_tiles;
+  p.rows = Tu;
+  p.cols = Tk;
+  p.out2 = out_f16;
+  p.K = K, p.U = U, p.C = C, p.Tk = Tk, p.Tu = Tu;
   return launch_gemm(ma, mb, p, (cudaStream_t)stream);
 }
 

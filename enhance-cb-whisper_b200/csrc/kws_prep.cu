@@ -180,6 +180,95 @@ __global__ void __launch_bounds__(256) resize_bilinear_kernel(const float* __res
 }
 
 // ---------------------------------------------------------------------------
+// Config #4 operand-side resize.  Bilinear resize (align_corners=False, no antialias) is linear and separable,
+// and the similarity image is bilinear in its operands, so
+//     resize(kwd . utt^T)[i, j] = < sum_r Wy[i, r] kwd[r], sum_x Wx[j, x] utt[x] >
+// The width map is applied to the utterance FRAMES before the GEMM (interp_rows_kernel: 1500 -> 750 frames is the
+// exact average of neighbours and halves the GEMM), the height map becomes a 64-wide operand of its own
+// (resize_weights_kernel) that the fused similarity+stem kernel contracts with the native-resolution similarity
+// (src/model/cb_whisper.py:189-210; torchvision resize == F.interpolate(bilinear, align_corners=False)).
+// ---------------------------------------------------------------------------
+constexpr int IR_MAX_V4 = 10;  // D <= 1280
+
+__device__ __forceinline__ void bilinear_tap(int i, int n_in, int n_out, int& i0, int& i1, float& w0, float& w1) {
+  const float s = (float)n_in / (float)n_out;
+  const float f = fmaxf(s * ((float)i + 0.5f) - 0.5f, 0.f);
+  i0 = min((int)f, n_in - 1);
+  i1 = i0 + (i0 < n_in - 1 ? 1 : 0);
+  w1 = f - (float)i0;
+  w0 = 1.f - w1;
+}
+
+// x fp32 [B,Cin,T,D] -> out fp16 [C,B,T_out,D]: out[j] = w0 * n(x[t0]) + w1 * n(x[t1]), n() = L2 normalisation
+__global__ void __launch_bounds__(256) interp_rows_kernel(const float* __restrict__ x, int B, int Cin, int T, int D,
+                                                          LayerIdx lidx, int C, int T_out, float eps,
+                                                          uint16_t* __restrict__ out) {
+  const int warps_per_block = blockDim.x >> 5;
+  const long long n_rows = (long long)C * B * T_out;
+  const int lane = threadIdx.x & 31;
+  const int nv4 = D >> 2;
+  for (long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < n_rows;
+       row += (long long)gridDim.x * warps_per_block) {
+    const int j = (int)(row % T_out);
+    const int b = (int)((row / T_out) % B);
+    const int c = (int)(row / ((long long)T_out * B));
+    int t0, t1;
+    float w0, w1;
+    bilinear_tap(j, T, T_out, t0, t1, w0, w1);
+    const float4* base = reinterpret_cast<const float4*>(x + ((long long)b * Cin + lidx.v[c]) * T * D);
+    const float4* s0 = base + (long long)t0 * nv4;
+    const float4* s1 = base + (long long)t1 * nv4;
+    float4 a[IR_MAX_V4], q[IR_MAX_V4];
+    float ssa = 0.f, ssq = 0.f;
+#pragma unroll
+    for (int i = 0; i < IR_MAX_V4; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nv4) {
+        a[i] = ldg_stream(s0 + idx);
+        q[i] = ldg_stream(s1 + idx);
+        ssa += a[i].x * a[i].x + a[i].y * a[i].y + a[i].z * a[i].z + a[i].w * a[i].w;
+        ssq += q[i].x * q[i].x + q[i].y * q[i].y + q[i].z * q[i].z + q[i].w * q[i].w;
+      }
+    }
+    const float ka = w0 / fmaxf(sqrtf(warp_sum(ssa)), eps), kq = w1 / fmaxf(sqrtf(warp_sum(ssq)), eps);
+    uint2* dst = reinterpret_cast<uint2*>(out + row * D);
+#pragma unroll
+    for (int i = 0; i < IR_MAX_V4; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nv4) {
+        uint2 o;
+        o.x = pack_half2(a[i].x * ka + q[i].x * kq, a[i].y * ka + q[i].y * kq);
+        o.y = pack_half2(a[i].z * ka + q[i].z * kq, a[i].w * ka + q[i].w * kq);
+        dst[idx] = o;
+      }
+    }
+  }
+}
+
+// Height map of the resize as an operand: out fp16 [C,K,Ho,Hp], row i = the two bilinear taps of output row i over
+// the src_h[k] valid frames of keyword k (columns >= src_h[k] are zero), the same for every layer c.
+__global__ void __launch_bounds__(256) resize_weights_kernel(const int32_t* __restrict__ src_h, int K, int C, int Hp,
+                                                             int Ho, __half* __restrict__ out) {
+  const long long total = (long long)C * K * Ho * Hp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i % Hp);
+    long long q = i / Hp;
+    const int row = (int)(q % Ho);
+    q /= Ho;
+    const int k = (int)(q % K);
+    const int h = src_h ? min(max(src_h[k], 1), Hp) : Hp;
+    int y0, y1;
+    float w0, w1;
+    bilinear_tap(row, h, Ho, y0, y1, w0, w1);
+    float v = 0.f;
+    if (r == y0) v += w0;
+    if (r == y1) v += w1;
+    out[i] = __float2half_rn(v);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // scores + top-k
 // ---------------------------------------------------------------------------
 __global__ void scores_kernel(const float* __restrict__ logits, const float* __restrict__ hw, size_t n,
@@ -325,6 +414,44 @@ int kws_resize_bilinear(const float* feat_f32, const int32_t* src_h, int K, int 
         out_f16 ? reinterpret_cast<__half*>(out_f16) + i0 * (long long)Ho * pitch16 : nullptr);
     KWS_CUDA(cudaGetLastError());
   }
+  return 0;
+}
+
+int kws_interp_rows(const float* x, int B, int Cin, int T, int D, const int32_t* layer_idx, int C, int T_out, float eps,
+                    void* out_f16, void* stream) {
+  KWS_CHECK_ARG(x && out_f16 && layer_idx, "interp_rows: null pointer");
+  KWS_CHECK_ARG(B > 0 && Cin > 0 && T > 0 && C > 0 && T_out > 0, "interp_rows: non-positive dimension");
+  KWS_CHECK_ARG(C <= MAX_LAYERS, "interp_rows: C=%d > %d", C, MAX_LAYERS);
+  KWS_CHECK_ARG(D % 8 == 0 && D <= IR_MAX_V4 * 128, "interp_rows: D=%d must be a multiple of 8 and <= %d", D,
+                IR_MAX_V4 * 128);
+  KWS_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out_f16) & 15) == 0,
+                "interp_rows: pointers must be 16-byte aligned");
+  LayerIdx li;
+  for (int i = 0; i < C; ++i) {
+    KWS_CHECK_ARG(layer_idx[i] >= 0 && layer_idx[i] < Cin, "interp_rows: layer_idx[%d]=%d out of [0,%d)", i,
+                  layer_idx[i], Cin);
+    li.v[i] = layer_idx[i];
+  }
+  const long long n_rows = (long long)C * B * T_out;
+  const int wpb = 8;
+  long long blocks = (n_rows + wpb - 1) / wpb;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  interp_rows_kernel<<<(int)blocks, wpb * 32, 0, (cudaStream_t)stream>>>(x, B, Cin, T, D, li, C, T_out, eps,
+                                                                        (uint16_t*)out_f16);
+  KWS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int kws_resize_row_weights(const int32_t* src_h, int K, int C, int Hp, int Ho, void* out_f16, void* stream) {
+  KWS_CHECK_ARG(out_f16, "resize_row_weights: null pointer");
+  KWS_CHECK_ARG(K > 0 && C > 0 && Hp > 0 && Ho > 0, "resize_row_weights: non-positive dimension");
+  const long long total = (long long)C * K * Ho * Hp;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  resize_weights_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(src_h, K, C, Hp, Ho, (__half*)out_f16);
+  KWS_CUDA(cudaGetLastError());
   return 0;
 }
 

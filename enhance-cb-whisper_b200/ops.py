@@ -12,7 +12,8 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import (BF16, F16, MLP_OUT_NORM_F16, MLP_OUT_RAW_16, MLP_OUT_RAW_F32, PAIRS_ALL, PAIRS_DIAG, STEM_OUT_NCHW_F32,
+from ._lib import (BF16, F16, MLP_OUT_NORM_F16, MLP_OUT_RAW_16, MLP_OUT_RAW_F32, PAIRS_ALL, PAIRS_DIAG, PAIRS_PER_KEYWORD,
+                   STEM_OUT_NCHW_F32,
                    STEM_OUT_NHWC_BF16, KWSError)
 
 TORCH16 = {F16: torch.float16, BF16: torch.bfloat16}
@@ -252,16 +253,21 @@ def sim_stem_supported(Cc: int, Tk: int, Tu: int, Dk: int, out_mode: int = STEM_
 
 def sim_stem(kwd_n: torch.Tensor, utt_n: torch.Tensor, w_fused: torch.Tensor, bias: torch.Tensor, out_mode: int,
              diag: bool = False, out: Optional[torch.Tensor] = None, k_range: Optional[Tuple[int, int]] = None,
-             u_range: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+             u_range: Optional[Tuple[int, int]] = None, per_keyword: bool = False) -> torch.Tensor:
     """Fused similarity + stem (w_fused from pack_stem_fused).  kwd_n fp16 [C,K,Tk,Dk], utt_n fp16 [C,U,Tu,Dk] -> stem activation of the
     pairs of keywords k_range=(k0,k1) x utterances u_range=(u0,u1) (default: all), pair = (k-k0)*(u1-u0) + (u-u0)
     (DIAG: pair = k-k0): NCHW fp32 [N,64,Ho,Wo] or channels_last bf16.  ``out`` may be a larger reused
-    buffer (its first N pairs are written)."""
+    buffer (its first N pairs are written).  ``per_keyword``: utt_n is [C, K*U, Tu, Dk], one utterance-side operand
+    per (keyword, utterance) (config #4: the native-resolution similarity, contracted with the resize's height map)."""
     lib = _lib.load()
     Cc, K, Tk, Dk = kwd_n.shape
     Cu, U, Tu, Dku = utt_n.shape
     if Cc != Cu or Dk != Dku:
         raise KWSError(f"operand mismatch: kwd {tuple(kwd_n.shape)} vs utt {tuple(utt_n.shape)}")
+    if per_keyword:
+        if diag or U % K != 0:
+            raise KWSError(f"per_keyword needs utt_n [C, K*U, Tu, Dk] (got {U} items for {K} keywords) and diag=False")
+        U //= K
     k0, k1 = k_range if k_range is not None else (0, K)
     u0, u1 = u_range if u_range is not None else (0, U)
     pairs = (k1 - k0) if diag else (k1 - k0) * (u1 - u0)
@@ -275,7 +281,9 @@ def sim_stem(kwd_n: torch.Tensor, utt_n: torch.Tensor, w_fused: torch.Tensor, bi
         if out.dtype != want or out.numel() < pairs * 64 * Ho * Wo:
             raise KWSError(f"out buffer too small / wrong dtype for {pairs} pairs")
     check(lib.kws_sim_stem_range(_cuda(kwd_n, "kwd_n", torch.float16), _cuda(utt_n, "utt_n", torch.float16), Cc, K,
-                                 U, Tk, Tu, Dk, PAIRS_DIAG if diag else PAIRS_ALL, k0, k1 - k0, u0, u1 - u0,
+                                 U, Tk, Tu, Dk,
+                                 PAIRS_PER_KEYWORD if per_keyword else (PAIRS_DIAG if diag else PAIRS_ALL), k0, k1 - k0,
+                                 u0, u1 - u0,
                                  _cuda(w_fused, "w_fused", torch.float16), _cuda(bias, "bias", torch.float32),
                                  out_mode, _cuda(out, "out"), _stream()), "kws_sim_stem", launches=(Cc + 11) // 12)
     shape = (pairs, 64, Ho, Wo) if f32 else (pairs, Ho, Wo, 64)
@@ -283,6 +291,44 @@ def sim_stem(kwd_n: torch.Tensor, utt_n: torch.Tensor, w_fused: torch.Tensor, bi
     if out_mode == STEM_OUT_NHWC_BF16:
         return view.permute(0, 3, 1, 2)
     return view
+
+
+def interp_rows(x: torch.Tensor, layer_idx: Sequence[int], T_out: int, eps: float = SIM_EPS) -> torch.Tensor:
+    """x fp32 [B,Cin,T,D] -> fp16 [C,B,T_out,D]: bilinear (align_corners=False) resampling of the L2-normalised
+    frames along T (config #4: the width map of the image resize applied to the utterance operand)."""
+    lib = _lib.load()
+    B, Cin, T, D = x.shape
+    Cc = len(layer_idx)
+    out = torch.empty((Cc, B, T_out, D), dtype=torch.float16, device=x.device)
+    check(lib.kws_interp_rows(_cuda(x, "x", torch.float32), B, Cin, T, D, _layers(layer_idx), Cc, int(T_out), eps,
+                              _cuda(out, "out"), _stream()), "kws_interp_rows")
+    return out
+
+
+def sim_operand(kwd_n: torch.Tensor, utt_n: torch.Tensor) -> torch.Tensor:
+    """kwd_n fp16 [C,K,Tk,Dk] (Tk % 16 == 0), utt_n fp16 [C,U,Tu,Dk] -> similarity as a K-major fp16 operand
+    [C, K*U, Tu, Tk] (item = k*U + u)."""
+    lib = _lib.load()
+    Cc, K, Tk, Dk = kwd_n.shape
+    Cu, U, Tu, Dku = utt_n.shape
+    if Cc != Cu or Dk != Dku:
+        raise KWSError(f"operand mismatch: kwd {tuple(kwd_n.shape)} vs utt {tuple(utt_n.shape)}")
+    out = torch.empty((Cc, K * U, Tu, Tk), dtype=torch.float16, device=kwd_n.device)
+    check(lib.kws_sim_operand(_cuda(kwd_n, "kwd_n", torch.float16), _cuda(utt_n, "utt_n", torch.float16), Cc, K, U, Tk,
+                              Tu, Dk, _cuda(out, "out"), _stream()), "kws_sim_operand")
+    return out
+
+
+def resize_row_weights(src_h: Optional[torch.Tensor], K: int, Cc: int, Hp: int, Ho: int, device=None) -> torch.Tensor:
+    """Height map of the bilinear resize as an operand: fp16 [C,K,Ho,Hp] (src_h int32 [K] valid frames, or None)."""
+    lib = _lib.load()
+    if src_h is not None and (src_h.dtype != torch.int32 or src_h.numel() != K):
+        raise KWSError("src_h must be int32 [K]")
+    dev = src_h.device if src_h is not None else device
+    out = torch.empty((Cc, K, Ho, Hp), dtype=torch.float16, device=dev)
+    check(lib.kws_resize_row_weights(_cuda(src_h, "src_h", torch.int32), K, Cc, Hp, Ho, _cuda(out, "out"), _stream()),
+          "kws_resize_row_weights")
+    return out
 
 
 def resize_bilinear(feat_f32: torch.Tensor, src_h: Optional[torch.Tensor], size: Tuple[int, int],

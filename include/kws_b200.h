@@ -48,6 +48,7 @@ extern "C" {
 /* kws_sim pair_mode */
 #define KWS_PAIRS_ALL 0
 #define KWS_PAIRS_DIAG 1
+#define KWS_PAIRS_PER_KEYWORD 2 /* kws_sim_stem only: utt_n holds one item per (keyword, utterance): [C, K*U, Tu, Dk] */
 
 /* kws_stem out_mode */
 #define KWS_STEM_OUT_NCHW_F32 0  /* fp32 [pairs,64,Ho,Wo]   (parity with the reference) */
@@ -186,6 +187,23 @@ int kws_sim_stem_range(const void* kwd_n, const void* utt_n, int C, int K, int U
  *   Requires U*C <= 65535 (whole keywords per launch).                                           */
 int kws_resize_bilinear(const float* feat_f32, const int32_t* src_h, int K, int U, int C, int Hs, int Ws, int Ho, int Wo,
                         float* out_f32, void* out_f16, int pitch16, void* stream);
+
+/* Config #4, operand-side resize (src/model/cb_whisper.py:189-210; torchvision resize(antialias=False) ==
+ * F.interpolate(bilinear, align_corners=False)).  The bilinear resize is linear and separable and the similarity
+ * image is bilinear in its operands, so resize(kwd . utt^T) = (Wy kwd) . (Wx utt)^T:
+ *   kws_interp_rows        applies Wx to the utterance frames: x fp32 [B,Cin,T,D] -> out fp16 [C,B,T_out,D], every
+ *                          source frame L2-normalised first (like kws_normalize_rows), D % 8 == 0, D <= 1280
+ *   kws_sim_operand        native-resolution similarity as a K-major fp16 operand: kwd_n [C,K,Tk,Dk] (Tk % 16 == 0,
+ *                          zero-padded frames), utt_n [C,U,Tu,Dk] -> out fp16 [C, K*U, Tu, Tk], item = k*U + u
+ *   kws_resize_row_weights Wy as an operand: out fp16 [C,K,Ho,Hp]; row i holds the two bilinear taps of output row i
+ *                          over the src_h[k] valid frames of keyword k (src_h DEVICE int32 [K] or NULL = Hp)
+ * and kws_sim_stem(kwd_n = Wy, utt_n = similarity operand, Dk = Hp = 64, KWS_PAIRS_PER_KEYWORD) contracts them and
+ * applies the stem: the resized [pairs,C,Ho,Wo] image never exists. */
+int kws_interp_rows(const float* x, int B, int Cin, int T, int D, const int32_t* layer_idx, int C, int T_out, float eps,
+                    void* out_f16, void* stream);
+int kws_sim_operand(const void* kwd_n, const void* utt_n, int C, int K, int U, int Tk, int Tu, int Dk, void* out_f16,
+                    void* stream);
+int kws_resize_row_weights(const int32_t* src_h, int K, int C, int Hp, int Ho, void* out_f16, void* stream);
 
 /* MaxPool2d(3, stride 2, padding 1) on the channels-last bf16 stem activation: the first op of the ResNet
  * body (HF modeling_resnet.py ResNetEmbeddings.pooler, reached through src/efficient_kws/resnet.py:53).

@@ -335,6 +335,78 @@ def test_resize_bilinear_matches_interpolate(ops, cuda_dev, K, U, Cc, Hs, Ws, si
     assert maxerr(o32b.flatten(0, 2), expb) <= 1e-5
 
 
+@pytest.mark.parametrize("B,Cin,T,D,T_out", [(2, 3, 40, 64, 20), (1, 2, 1500, 1024, 750), (2, 2, 31, 128, 50), (1, 1, 7, 1280, 7)])
+def test_interp_rows_matches_interpolate(ops, cuda_dev, B, Cin, T, D, T_out):
+    """Width map of the config-#4 resize applied to the (normalised) utterance frames."""
+    g = gen(cuda_dev)
+    x = torch.randn(B, Cin, T, D, generator=g, device=cuda_dev) * 3
+    idx = list(range(Cin))[::-1]
+    got = ops.interp_rows(x, idx, T_out)
+    xn = torch.nn.functional.normalize(x[:, idx], dim=-1)  # [B,C,T,D]
+    exp = torch.nn.functional.interpolate(xn.flatten(0, 1).transpose(1, 2), size=T_out, mode="linear",
+                                          align_corners=False).transpose(1, 2).view(B, Cin, T_out, D).transpose(0, 1)
+    assert got.shape == (Cin, B, T_out, D) and got.dtype == torch.float16
+    assert maxerr(got, exp) <= 6e-4
+
+
+def test_resize_row_weights_are_the_bilinear_taps(ops, cuda_dev):
+    lens = torch.tensor([1, 5, 17, 33, 64, 10], dtype=torch.int32, device=cuda_dev)
+    K, Cc, Hp, Ho = lens.numel(), 2, 64, 150
+    wy = ops.resize_row_weights(lens, K, Cc, Hp, Ho)
+    assert wy.shape == (Cc, K, Ho, Hp)
+    for k, h in enumerate(lens.tolist()):
+        eye = torch.eye(h, device=cuda_dev)[None, None]  # resize of the identity = the map itself
+        exp = torch.nn.functional.interpolate(eye, size=(Ho, h), mode="bilinear", align_corners=False)[0, 0]
+        for c in range(Cc):
+            assert maxerr(wy[c, k, :, :h], exp) <= 5e-4
+            assert float(wy[c, k, :, h:].abs().max()) == 0.0 if h < Hp else True
+
+
+def test_sim_operand_is_the_transposed_similarity(ops, cuda_dev):
+    g = gen(cuda_dev)
+    Cc, K, U, Tk, Tu, Dk = 3, 4, 2, 64, 200, 128
+    kn = unit_rows(Cc, K, Tk, Dk, g=g, dev=cuda_dev).half()
+    kn[:, 1, 20:] = 0
+    un = unit_rows(Cc, U, Tu, Dk, g=g, dev=cuda_dev).half()
+    got = ops.sim_operand(kn, un)  # [C, K*U, Tu, Tk]
+    exp = torch.einsum("cutd,ckid->ckuti", un.float(), kn.float()).reshape(Cc, K * U, Tu, Tk)
+    assert got.shape == exp.shape
+    assert maxerr(got, exp) <= 1e-3
+    assert float(got.view(Cc, K, U, Tu, Tk)[:, 1, :, :, 20:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("size,Tu,lens", [((30, 50), 100, (9, 21, 14, 64, 1)), ((150, 750), 1500, (10, 60))])
+def test_cbw_fused_stem_never_builds_the_image(built_lib, cuda_dev, size, Tu, lens):
+    """Config #4 scoring path: (Wy kwd) . (Wx utt)^T inside the fused kernel == stem of the restated
+    cb_whisper.py:189-210 images (bf16 output; operand-side resize adds two fp16 roundings)."""
+    from enhance_cb_whisper_b200 import Resnet, cbw, ops as _ops
+
+    torch.manual_seed(5)
+    g = torch.Generator().manual_seed(13)
+    Cc, D, S = 12, 64, 2
+    resnet = Resnet(Cc, 2, "resnet-18").eval()
+    bn = resnet.feature_extractor.embedder.embedder.normalization
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(64, generator=g) + 0.5), bn.bias.copy_(torch.randn(64, generator=g) * 0.1)
+        bn.running_mean.copy_(torch.randn(64, generator=g) * 0.1), bn.running_var.copy_(torch.rand(64, generator=g) + 0.5)
+    kwd_list = [torch.nn.functional.normalize(torch.randn(Cc, t, D, generator=g), dim=-1) for t in lens]
+    utt = torch.nn.functional.normalize(torch.randn(S, Cc, Tu, D, generator=g), dim=-1)
+    with torch.inference_mode():
+        imgs = O.cbw_similarity_resized(kwd_list, utt, size=size)  # [K,S,C,h,w]
+        exp = resnet.feature_extractor.embedder.embedder(imgs.flatten(0, 1))  # conv + BN + ReLU
+    sp = cbw.CBWKeywordSpotterB200(resnet.to(cuda_dev), size=size)
+    kwd_n, lens_t = cbw.pack_keywords([k.to(cuda_dev) for k in kwd_list], cuda_dev, multiple=64)
+    utt_i = _ops.interp_rows(utt.to(cuda_dev), list(range(Cc)), size[1])
+    got = []
+    sp.stem_fused(kwd_n, lens_t, utt_i, _ops.STEM_OUT_NCHW_F32, max_pairs=4, consume=lambda k0, k1, st: got.append(st.clone()))
+    got = torch.cat(got)
+    assert got.shape == exp.shape
+    assert maxerr(got.cpu(), exp) <= 3e-3 * max(1.0, exp.abs().max().item())
+    got16 = []
+    sp.stem_fused(kwd_n, lens_t, utt_i, _ops.STEM_OUT_NHWC_BF16, max_pairs=64, consume=lambda k0, k1, st: got16.append(st.float()))
+    assert maxerr(torch.cat(got16).cpu(), exp) <= 2e-2 * max(1.0, exp.abs().max().item() / 4)
+
+
 def test_cbw_similarity_images_match_oracle(built_lib, cuda_dev):
     """B200 config-#4 path == restated cb_whisper.py:189-210 (ragged keywords, matmul, bilinear resize)."""
     from enhance_cb_whisper_b200 import cbw
@@ -370,8 +442,11 @@ def test_cbw_keyword_spotter_logits_and_detections(built_lib, cuda_dev):
         imgs = O.cbw_similarity_resized(kwd_list, utt, size=size)  # [K,S,C,h,w]
         exp = resnet(imgs.flatten(0, 1)).view(len(kwd_list), S, 2)
     sp = cbw.CBWKeywordSpotterB200(resnet.to(cuda_dev), size=size)
-    got = sp.logits([k.to(cuda_dev) for k in kwd_list], utt.to(cuda_dev))
+    got = sp.logits([k.to(cuda_dev) for k in kwd_list], utt.to(cuda_dev), fused=False)  # images + un-fused stem
     assert maxerr(got.cpu(), exp) <= 2e-3
+    assert sp.fused_ok(kwd_list, utt.to(cuda_dev))
+    got = sp.logits([k.to(cuda_dev) for k in kwd_list], utt.to(cuda_dev))  # fused: the image is never built
+    assert maxerr(got.cpu(), exp) <= 4e-3
     det = sp.detect([k.to(cuda_dev) for k in kwd_list], utt.to(cuda_dev))
     exp_hit = exp.argmax(-1) == 1
     margin = (exp[..., 1] - exp[..., 0]).abs().min().item()

@@ -31,5 +31,6 @@ print(f"per item (mean over CTAs, {items:.1f} items/CTA): total {b[0]/items:.0f}
       f"aempty wait {b[2]/items:.0f} | qfull wait {b[3]/items:.0f} | issue {b[4]/items:.0f}")
 print(f"  epilogue: afull wait {b[5]/items:.0f} | until acc released {b[6]/items:.0f} | whole step body {b[7]/items:.0f}")
 print(f"  converter: sfull wait {b[8]/items:.0f} | tmem ld {b[9]/items:.0f} | qempty wait {b[10]/items:.0f} | pack+store {b[11]/items:.0f}")
+print(f"  multi-pass epilogue: partial-sum load wait {b[12]/items:.0f} | LDS of the partial tile {b[13]/items:.0f}")
 print("  epilogue phases per item: " + " | ".join(f"{n} {b[16+i]/items:.0f}" for i, n in enumerate(
     ["g0 ld+wait", "g0 mbox+bar", "g0 shfl+math+sts", "g1 ld+wait", "g1 mbox+bar", "g1 shfl+math+sts", "fence+tma"])))
