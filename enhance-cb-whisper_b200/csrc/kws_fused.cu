@@ -297,6 +297,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
         const ItemCoord w = decode_item(p, it);
         const int jbase = 2 * G_TILE_OJ * w.ct - 3;  // input column of pixel x = 0 (OOB columns read as zero)
         for (int n = 0; n < p.n_chunks; ++n) {
+          if (ROWS * n - 3 >= p.Tk) continue;  // chunk entirely below the image (conv zero padding): nothing to load
           for (int c = 0; c < p.C; ++c) {
             for (int kb = 0; kb < p.nkb; ++kb) {
               mbar_wait(&oempty[stage], phase ^ 1, 100 + stage);
@@ -326,6 +327,15 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
       [[maybe_unused]] uint32_t tr_s = 0;
       for (long long it = blockIdx.x; it < p.num_items; it += gridDim.x) {
         for (int n = 0; n < p.n_chunks; ++n, ++g) {
+          if (ROWS * n - 3 >= p.Tk) {
+            // all-zero chunk: no operands, no MMAs; keep the tile hand-shake (the converters write zeros without
+            // reading the tiles)
+            for (int j = 0; 2 * j < p.C; ++j) {
+              mbar_wait(&sempty[j], (g & 1) ^ 1, 500 + j);
+              umma_commit(&sfull[j]);
+            }
+            continue;
+          }
           for (int st = 0; st < stages_per_chunk; ++st) {
             const int c = st / p.nkb, kb = st - c * p.nkb;
             // the converters have pulled the previous chunk's tiles of this layer pair out of TMEM
@@ -701,7 +711,12 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
         uint32_t h2[ROWS][NPAIR];  // [row][layer pair] fp16x2
 #pragma unroll
         for (int j = 0; j < NPAIR; ++j) {
-          if (2 * j < p.C) {
+          if (2 * j < p.C && 4 * q0 - 3 >= p.Tk) {  // chunk entirely below the image: zeros, tiles untouched
+            mbar_wait(&sfull[j], g & 1, 700 + j);
+            mbar_arrive(&sempty[j]);
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) h2[r][j] = 0u;
+          } else if (2 * j < p.C) {
             mbar_wait(&sfull[j], g & 1, 700 + j);
             tc_fence_after();
 #pragma unroll
