@@ -111,6 +111,8 @@ struct FusedParams {
   int c0;        // first layer of this pass in the operand banks (C layers [c0, c0+C) are processed)
   int C_total;   // layers in the operand banks (tensor-map batch = layer * bank size + item)
   int acc_mode;  // 0 single pass | 1 first pass: write fp16 partial sums | 2 middle: += | 3 last: +=, bias, ReLU, bf16
+  int reduce_mid;  // middle passes add their partial sums with a TMA reduce-add store (fp16 add in L2) instead of
+                   // loading the previous sums, adding in registers and storing
   int n_mma;     // stem MMAs per kernel row: 2 (C <= 8) or 3
   int nP;        // stem steps per item = ceil(Ho / 2)
   int nQ;        // quanta (4 input rows) converted per item = nP + 2
@@ -475,6 +477,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
     uint32_t acc_seq = 0;
+    const bool loads_prev = MULTI && (p.acc_mode == 3 || (p.acc_mode == 2 && !p.reduce_mid));
     uint32_t pl_seq[2] = {0u, 0u};  // partial-sum tiles consumed so far from each staging set (phase of pload[q][set])
     // Partial sums of the previous channel-group pass: the tile of step n+1 is TMA-loaded into the other staging set
     // while step n is processed (a load issued and awaited inside one step would put its whole latency, ~2 k cycles
@@ -489,7 +492,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
           : "memory");
     };
     auto tile_ok_at = [&](int ct, int oi) { return oi < p.Ho && ct * G_TILE_OJ + (q & 1) * 32 < p.Wo; };
-    if (MULTI && nhwc && p.prefetch == 1 && p.acc_mode >= 2 && lane == 0 && (long long)blockIdx.x < p.num_items) {
+    if (MULTI && nhwc && p.prefetch == 1 && loads_prev && lane == 0 && (long long)blockIdx.x < p.num_items) {
       const ItemCoord w0 = decode_item(p, blockIdx.x);
       if (tile_ok_at(w0.ct, row_sel)) load_prev(0u, w0.ct, row_sel, (int)w0.pair);
     }
@@ -536,7 +539,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
             // the previous step's TMA store must have read this warp's staging buffer before it is reused
             if (lane == 0) {
               asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-              if (nhwc && MULTI && p.acc_mode >= 2 && p.prefetch != 1) {
+              if (nhwc && MULTI && loads_prev && p.prefetch != 1) {
                 if (tile_ok) load_prev(0u, w.ct, oi, (int)w.pair);  // awaited below, in this step
                 if (p.prefetch == 2) {  // next step's tile: HBM -> L2 now, so that its load is an L2 hit
                   int nct = w.ct, noi = oi + 2, npair = (int)w.pair;
@@ -551,7 +554,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
                                  "r"(0), "r"(nct * G_TILE_OJ + (q & 1) * 32), "r"(noi), "r"(npair)
                                  : "memory");
                 }
-              } else if (nhwc && MULTI && p.acc_mode >= 2) {
+              } else if (nhwc && MULTI && loads_prev) {
                 // the other staging set is free now (its store has been read): prefetch the next step's partial sums
                 if (P + 1 < p.nP) {
                   if (tile_ok_at(w.ct, oi + 2)) load_prev(set ^ 1u, w.ct, oi + 2, (int)w.pair);
@@ -603,7 +606,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
             const int ch = grp * NH + h;
             if constexpr (nhwc) {
               const bool with_bias = !MULTI || p.acc_mode == 0 || p.acc_mode == 3;  // single or last channel-group pass
-              const bool add_prev = MULTI && p.acc_mode >= 2 && tile_ok;
+              const bool add_prev = MULTI && loads_prev && tile_ok;
               uint8_t* c0p = srow + (((2 * ch) ^ (lane & 7)) << 4);
               uint8_t* c1p = srow + (((2 * ch + 1) ^ (lane & 7)) << 4);
               uint32_t prev[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
@@ -663,15 +666,24 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
           tp[7] = f2;
         }
         if constexpr (nhwc) {
-          if (MULTI && p.acc_mode >= 2 && tile_ok) ++pl_seq[set];
+          if (MULTI && loads_prev && tile_ok) ++pl_seq[set];
           fence_proxy_async();
           __syncwarp();
           if (lane == 0 && tile_ok) {
-            asm volatile(
-                "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
-                    reinterpret_cast<uint64_t>(my_map)),
-                "r"(smem_u32(my_stage)), "r"(0), "r"(w.ct * G_TILE_OJ + (q & 1) * 32), "r"(oi), "r"((int)w.pair)
-                : "memory");
+            if (MULTI && p.acc_mode == 2 && p.reduce_mid) {
+              // out (fp16 partial sums of the earlier passes) += this pass's partial sums, added where the data lives
+              asm volatile(
+                  "cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                      reinterpret_cast<uint64_t>(my_map)),
+                  "r"(smem_u32(my_stage)), "r"(0), "r"(w.ct * G_TILE_OJ + (q & 1) * 32), "r"(oi), "r"((int)w.pair)
+                  : "memory");
+            } else {
+              asm volatile(
+                  "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                      reinterpret_cast<uint64_t>(my_map)),
+                  "r"(smem_u32(my_stage)), "r"(0), "r"(w.ct * G_TILE_OJ + (q & 1) * 32), "r"(oi), "r"((int)w.pair)
+                  : "memory");
+            }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
@@ -866,7 +878,8 @@ static int fused_n_mma(int C) { return C <= 8 ? 2 : 3; }
 // C > 12 layers are processed in passes over channel groups of 12 layers; the passes chain their
 // partial sums through the output buffer itself (fp16, same tiles), the last one adds bias + ReLU -> bf16.
 constexpr int G_MAX_C_TOTAL = 64;
-static int g_multi_group = 12, g_multi_nh = 2, g_multi_prefetch = 2;
+static int g_multi_group = 12, g_multi_nh = 2, g_multi_prefetch = 2, g_multi_reduce = 1;
+extern "C" void kws_debug_set_fused_reduce(int on) { g_multi_reduce = on ? 1 : 0; }
 // Multi-pass variants (development aid; measured at the cfg3 slab, pairs/s): layers per pass 12 | 8, output
 // channels / 16 per epilogue TMEM round trip 2 | 1, partial-sum prefetch 0 none | 1 into a second staging set
 // (8-layer groups only: their smaller weights leave the 16 KB free) | 2 into L2 only.
@@ -883,8 +896,10 @@ static void multi_cfg_from_env() {  // development aid: KWS_FUSED_MULTI="group,n
   if (done) return;
   done = true;
   if (const char* e = getenv("KWS_FUSED_MULTI")) {
-    int g = 8, nh = 1, pf = 1;
-    if (sscanf(e, "%d,%d,%d", &g, &nh, &pf) == 3) kws_debug_set_fused_multi(g, nh, pf);
+    int g = 8, nh = 1, pf = 1, red = 1;
+    const int n = sscanf(e, "%d,%d,%d,%d", &g, &nh, &pf, &red);
+    if (n >= 3) kws_debug_set_fused_multi(g, nh, pf);
+    if (n == 4) kws_debug_set_fused_reduce(red);
   }
 }
 static int fused_group_size(int C) {
@@ -967,7 +982,7 @@ extern "C" int kws_sim_stem_range(const void* kwd_n, const void* utt_n, int C, i
   const int Ho = (Tk + 1) / 2, Wo = (Tu + 1) / 2;
   const long long n_pairs = (long long)nk * (pair_mode == KWS_PAIRS_DIAG ? 1 : nu);
   KWS_CHECK_ARG(n_pairs < (1ll << 31), "sim_stem: too many pairs in one launch");
-  CUtensorMap mo_lo, mo_hi;
+  CUtensorMap mo_lo, mo_hi, mo_lo_f16, mo_hi_f16;  // *_f16: the same tiles typed fp16 (element type of the reduce-add)
   {
     // bf16 channels-last activation [pairs, Ho, Wo, 64]; one box = 32 (lo warp) or 28 (hi warp: slots 32..59)
     // pixels x 64 channels of one output row.  (Encoded for the fp32 NCHW mode as well, where it is not used.)
@@ -978,6 +993,12 @@ extern "C" int kws_sim_stem_range(const void* kwd_n, const void* utt_n, int C, i
                                 CU_TENSOR_MAP_SWIZZLE_128B))
       return e;
     if (int e = make_tensor_map(&mo_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, dims, strides, box_hi,
+                                CU_TENSOR_MAP_SWIZZLE_128B))
+      return e;
+    if (int e = make_tensor_map(&mo_lo_f16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, out, dims, strides, box_lo,
+                                CU_TENSOR_MAP_SWIZZLE_128B))
+      return e;
+    if (int e = make_tensor_map(&mo_hi_f16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, out, dims, strides, box_hi,
                                 CU_TENSOR_MAP_SWIZZLE_128B))
       return e;
   }
@@ -1037,7 +1058,9 @@ extern "C" int kws_sim_stem_range(const void* kwd_n, const void* utt_n, int C, i
     }
     const size_t smem = g_smem_bytes(rows, p.n_mma, p.acc_mode != 0 && p.prefetch == 1);
     KWS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(int)grid, G_THREADS, smem, (cudaStream_t)stream>>>(mu, mk, mo_lo, mo_hi, p);
+    p.reduce_mid = g_multi_reduce;
+    const bool red = p.acc_mode == 2 && p.reduce_mid;
+    kern<<<(int)grid, G_THREADS, smem, (cudaStream_t)stream>>>(mu, mk, red ? mo_lo_f16 : mo_lo, red ? mo_hi_f16 : mo_hi, p);
     KWS_CUDA(cudaGetLastError());
     wsrc += fused_group_bytes(Cg);
   }

@@ -465,6 +465,7 @@ def test_sim_stem_fused_channel_groups(ops, cuda_dev, Cc, K, U, Tk, Tu, multi):
 
     lib = _lib.load()
     lib.kws_debug_set_fused_multi(*multi)
+    lib.kws_debug_set_fused_reduce(0 if multi == (12, 2, 0) else 1)  # middle passes: TMA reduce-add (default) | load+add
     try:
         g = gen(cuda_dev)
         kn = unit_rows(Cc, K, Tk, 64, g=g, dev=cuda_dev).half()
@@ -483,3 +484,4 @@ def test_sim_stem_fused_channel_groups(ops, cuda_dev, Cc, K, U, Tk, Tu, multi):
             ops.sim_stem(kn, un, wf, bias, ops.STEM_OUT_NCHW_F32)
     finally:
         lib.kws_debug_set_fused_multi(12, 2, 2)
+        lib.kws_debug_set_fused_reduce(1)
