@@ -1,6 +1,2 @@
-timeout 400 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_model.py -m gpu -x -q -k "channel_groups or many_layers" > gpurun_out/pytest_gpu.log 2>&1; tail -6 gpurun_out/pytest_gpu.log
-for v in "12,2,2,0" "12,2,2,1" "12,2,2,0" "12,2,2,1"; do
-  KWS_FUSED_MULTI=$v timeout 200 python bench.py --workload cfg3 --no-cpu --no-e2e --steps 2 --warmup 3 > gpurun_out/ab.json 2> gpurun_out/ab.err || tail -3 gpurun_out/ab.err
-  python -c "
-import json; d=json.load(open('gpurun_out/ab.json')); print('$v', round(d['value']), d['phases_ms']['pairs_ms'], d['roofline']['frac'])"
-done 2>&1 | tee gpurun_out/ab_reduce.log
+timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
+timeout 300 python tools/ab_fused.py enhance-cb-whisper_b200/libkws_b200_head.so enhance-cb-whisper_b200/libkws_b200.so enhance-cb-whisper_b200/libkws_b200_head.so enhance-cb-whisper_b200/libkws_b200.so 2>&1 | tee gpurun_out/ab_mailbox.log | tail -12
