@@ -67,6 +67,26 @@ UNIT = "pairs/s"
 SEED = 123  # seed_everything: 123 in the reference YAMLs
 
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version / NCCL_DEBUG output to
+# stdout), so file descriptor 1 is pointed at stderr for the life of the process and the line goes to a private
+# duplicate of the original stdout.
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -316,7 +336,7 @@ def run_reference_arm(args, wl):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t_start,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -567,7 +587,7 @@ def run_b200_arm(args, wl):
             "phases_ms": phases, "projection_tflops": proj_tflops, "hbm": hbm,
             "wall_s": time.perf_counter() - t_start,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -598,4 +618,5 @@ def main():
 
 
 if __name__ == "__main__":
+    claim_stdout()
     main()
