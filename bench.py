@@ -603,7 +603,7 @@ def main():
     ap.add_argument("--utts", type=int, default=0, help="override U (utterances)")
     ap.add_argument("--max-pairs", type=int, default=1184, help="pairs per similarity+stem launch (8 x 148)")
     ap.add_argument("--e2e-utts", type=int, default=8, help="utterances per e2e step")
-    ap.add_argument("--e2e-pairs", type=int, default=250, help="pairs per body chunk in the e2e path")
+    ap.add_argument("--e2e-pairs", type=int, default=500, help="pairs per body chunk in the e2e path")
     ap.add_argument("--e2e-slab", type=int, default=125, help="keywords per H2D slab in the e2e path")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -8,7 +8,9 @@ eps of the module) and each convolution is issued as ONE cuDNN fused op,
 
     conv + bias + ReLU                 torch.cudnn_convolution_relu
     conv + residual + bias + ReLU      torch.cudnn_convolution_add_relu   (last conv of a residual layer)
-    conv + bias                        F.conv2d                            (projection shortcut, no activation)
+    conv                               F.conv2d                            (projection shortcut; its folded bias is
+                                                                            added to the bias of the residual
+                                                                            layer's last conv, so no bias pass)
 
 on channels-last 16-bit activations.  Not part of the hot path of SURVEY.md section 8; it bounds the end-to-end
 number, which is why it is worth running well.  CUDA only.
@@ -45,8 +47,8 @@ class _Conv:
     def add_relu(self, x, z):
         return torch.cudnn_convolution_add_relu(x, self.w, z, 1.0, self.b, self.stride, self.padding, (1, 1), 1)
 
-    def plain(self, x):
-        return F.conv2d(x, self.w, self.b, self.stride, self.padding)
+    def plain(self, x):  # bias-free: the caller has moved self.b into the consumer's bias
+        return F.conv2d(x, self.w, None, self.stride, self.padding)
 
 
 class FusedBody:
@@ -65,7 +67,14 @@ class FusedBody:
             layers = []
             for layer in stage.layers:
                 sc = None if isinstance(layer.shortcut, nn.Identity) else _Conv(layer.shortcut, dtype)
-                layers.append((sc, [_Conv(cl, dtype) for cl in layer.layer]))
+                convs = [_Conv(cl, dtype) for cl in layer.layer]
+                if sc is not None:
+                    # relu(conv3(h) + b3 + (shortcut(x) + bs)) == relu(conv3(h) + (b3 + bs) + shortcut_nobias(x)):
+                    # torch's conv2d-with-bias is a convolution plus an elementwise pass over the widest tensor of the block
+                    _, b_sc = _fold(layer.shortcut.convolution, layer.shortcut.normalization, torch.float32)
+                    _, b_last = _fold(layer.layer[-1].convolution, layer.layer[-1].normalization, torch.float32)
+                    convs[-1].b = (b_last + b_sc).to(dtype).contiguous()
+                layers.append((sc, convs))
             self.stages.append(layers)
         lin = resnet.classifier[1]
         self.lin_w = lin.weight.detach().float()
