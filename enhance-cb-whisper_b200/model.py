@@ -88,6 +88,11 @@ def run_body(resnet: nn.Module, stem_activation: torch.Tensor) -> torch.Tensor:
     return resnet.classifier(torch.flatten(x, 1).float())
 
 
+def _empty_scores(K: int, U: int, device):
+    return (torch.empty((K, U), dtype=torch.float32, device=device), torch.empty((K, U), dtype=torch.uint8, device=device),
+            torch.empty((K, U, 2), dtype=torch.float32, device=device))
+
+
 class _HParams(dict):
     __getattr__ = dict.__getitem__
     __setattr__ = dict.__setitem__
@@ -216,7 +221,10 @@ class B200ForwardMixin:
     def score(self, kwd_features, utt_features, kwd_mask, utt_mask, hotword_mask=None, max_pairs: int = 256,
               threshold: Optional[float] = None):
         """All K x U pairs -> (scores [K,U], detections uint8 [K,U], logits [K,U,2]).
-        score = softmax(logits)[:,1] * hotword_mask (model.py:783-795)."""
+        score = softmax(logits)[:,1] * hotword_mask (model.py:783-795).  An empty keyword or utterance batch
+        returns empty results (the reference's group loop simply does not iterate)."""
+        if kwd_features.shape[0] == 0 or utt_features.shape[0] == 0:
+            return _empty_scores(kwd_features.shape[0], utt_features.shape[0], kwd_features.device)
         eng = self.prepare(kwd_features.device)
         layer_idx = list(self.b200_layer_idx) if self.b200_layer_idx is not None else list(range(self.hparams.n_layers))
         kwd_n = eng.compress(kwd_features, kwd_mask, layer_idx)
@@ -232,6 +240,8 @@ class B200ForwardMixin:
         transfer of the raw fp32 embeddings (the largest tensor of the job: K x C x Tk x D x 4 bytes) hides
         behind the compute.  Returns device tensors like ``score``."""
         dev = torch.device(device) if device is not None else next(self.parameters()).device
+        if kwd_features.shape[0] == 0 or utt_features.shape[0] == 0:
+            return _empty_scores(kwd_features.shape[0], utt_features.shape[0], dev)
         eng = self.prepare(dev)
         layer_idx = list(self.b200_layer_idx) if self.b200_layer_idx is not None else list(range(self.hparams.n_layers))
         K, U = kwd_features.shape[0], utt_features.shape[0]

@@ -66,3 +66,15 @@ def test_fused_body_refuses_cpu_tensors():
     fb = body.FusedBody(Resnet(12, 2, "resnet-18").eval(), torch.float32)
     with pytest.raises(RuntimeError):
         fb(torch.zeros(1, 64, 8, 8))
+
+
+def test_score_of_an_empty_batch_is_empty():
+    """K = 0 keywords or U = 0 utterances: empty results, no kernel launch (also without a GPU)."""
+    import enhance_cb_whisper_b200 as kb
+
+    m = kb.KWSModelB200(n_layers=2, embedding_dim=64, learn_features=False)
+    kwd, utt = torch.zeros(0, 2, 10, 64), torch.zeros(3, 2, 40, 64)
+    sc, det, lg = m.score(kwd, utt, torch.zeros(0, 2, 10), torch.zeros(3, 2, 40))
+    assert sc.shape == (0, 3) and det.shape == (0, 3) and lg.shape == (0, 3, 2) and det.dtype == torch.uint8
+    sc, det, lg = m.score_host(utt, kwd, torch.zeros(3, 2, 40), torch.zeros(0, 2, 10), device="cpu")
+    assert sc.shape == (3, 0) and lg.shape == (3, 0, 2)
