@@ -1,5 +1,7 @@
-for v in "12,2,2,1,0" "12,2,2,1,1" "12,2,2,1,0" "12,2,2,1,1"; do
-  KWS_FUSED_MULTI=$v timeout 200 python bench.py --workload cfg3 --no-cpu --no-e2e --steps 2 --warmup 3 > gpurun_out/ab.json 2> gpurun_out/ab.err || tail -3 gpurun_out/ab.err
-  python -c "
-import json; d=json.load(open('gpurun_out/ab.json')); print('$v', round(d['value']), d['phases_ms']['pairs_ms'], d['roofline']['frac'])"
-done 2>&1 | tee gpurun_out/ab_order.log
+# round-end style validation on one B200: GPU tests, smoke, both bench arms (default flags)
+timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 400 python bench.py --impl reference > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -c 700 gpurun_out/bench_ref.json; echo
+timeout 400 python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; tail -1 gpurun_out/bench_full.err
+python -c "
+import json; d=json.load(open('gpurun_out/bench_full.json')); print(d['value'], d['e2e']['value'], d['e2e']['ms_per_step'], d['roofline']['frac'], d['cpu_baseline']['value'], d['cpu_baseline']['cores'], d['gpu_launches'], d['clocks'], d['wall_s'])"
