@@ -6,9 +6,9 @@ from enhance_cb_whisper_b200 import ops, _lib
 
 dev = torch.device("cuda:0")
 g = torch.Generator(device=dev).manual_seed(7)
-# usage: fused_counters.py [C Tk Tu K U]   (default: the cfg2 shape; C > 12 reports the LAST channel-group pass)
+# usage: fused_counters.py [C Tk Tu K U [Dk]]   (default: the cfg2 shape; C > 12 reports the LAST channel-group pass)
 Cc, Tk, Tu, K, U = (int(a) for a in sys.argv[1:6]) if len(sys.argv) >= 6 else (12, 150, 1500, 74, 2)
-P = 64
+P = int(sys.argv[6]) if len(sys.argv) >= 7 else 64
 Ho, Wo = (Tk + 1) // 2, (Tu + 1) // 2
 unit = lambda *s: torch.nn.functional.normalize(torch.randn(*s, generator=g, device=dev), dim=-1)
 kn, un = unit(Cc, K, Tk, P).half(), unit(Cc, U, Tu, P).half()

@@ -1,7 +1,9 @@
-# round-end style validation on one B200: GPU tests, smoke, both bench arms (default flags)
-timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-timeout 400 python bench.py --impl reference > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -c 700 gpurun_out/bench_ref.json; echo
-timeout 400 python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; tail -1 gpurun_out/bench_full.err
-python -c "
-import json; d=json.load(open('gpurun_out/bench_full.json')); print(d['value'], d['e2e']['value'], d['e2e']['ms_per_step'], d['roofline']['frac'], d['cpu_baseline']['value'], d['cpu_baseline']['cores'], d['gpu_launches'], d['clocks'], d['wall_s'])"
+cp enhance-cb-whisper_b200/libkws_b200.so /tmp/new.so
+for wl in cfg1 cfg3; do
+  for lib in new head new head; do
+    if [ $lib = new ]; then cp /tmp/new.so enhance-cb-whisper_b200/libkws_b200.so; else cp enhance-cb-whisper_b200/libkws_b200_head.so enhance-cb-whisper_b200/libkws_b200.so; fi
+    timeout 200 python bench.py --workload $wl --no-cpu --no-e2e --steps 3 --warmup 3 > gpurun_out/ab.json 2> gpurun_out/ab.err || tail -3 gpurun_out/ab.err
+    python -c "
+import json; d=json.load(open('gpurun_out/ab.json')); print('$wl $lib', round(d['value']), d['roofline']['frac'], d['clocks']['sm_mhz'])"
+  done
+done 2>&1 | tee gpurun_out/ab_wg2.log
