@@ -6,7 +6,10 @@ from enhance_cb_whisper_b200 import ops, _lib
 
 dev = torch.device("cuda:0")
 g = torch.Generator(device=dev).manual_seed(7)
+# usage: fused_trace.py [grid_limit [C Dk]]
 Cc, K, U, Tk, Tu, P = 12, 74, 2, 150, 1500, 64
+if len(sys.argv) > 3:
+    Cc, P = int(sys.argv[2]), int(sys.argv[3])
 unit = lambda *s: torch.nn.functional.normalize(torch.randn(*s, generator=g, device=dev), dim=-1)
 kn, un = unit(Cc, K, Tk, P).half(), unit(Cc, U, Tu, P).half()
 wp, bias = ops.pack_stem_fused(torch.randn(64, Cc, 7, 7, generator=g, device=dev) * 0.05, torch.ones(64, device=dev),
@@ -16,7 +19,7 @@ ops.sim_stem(kn, un, wp, bias, ops.STEM_OUT_NHWC_BF16, out=out)
 TS = 640
 buf = torch.zeros(148 * 32 + 4 * TS * 8, dtype=torch.int64, device=dev)
 lib = _lib.load()
-if len(sys.argv) > 1:
+if len(sys.argv) > 1 and int(sys.argv[1]) > 0:
     lib.kws_debug_set_fused_grid_limit(int(sys.argv[1]))
     print('grid limit', sys.argv[1])
 lib.kws_debug_set_fused_counters.argtypes = [ctypes.c_void_p]
