@@ -1,5 +1,5 @@
-KWS_FUSED_TIMERS=1 python enhance-cb-whisper_b200/build.py > /dev/null 2>&1
-timeout 120 python tools/fused_trace.py 0 12 64 > gpurun_out/trace_cfg2.log 2>&1
-timeout 120 python tools/fused_trace.py 0 4 384 > gpurun_out/trace_cfg1.log 2>&1
-timeout 120 python tools/fused_trace.py 0 4 64 > gpurun_out/trace_c4.log 2>&1
-head -30 gpurun_out/trace_cfg1.log
+for c in 8 6; do for ns in 0 4 0 4; do
+  echo -n "C=$c NS=$ns: "; KWS_FUSED_NS=$ns timeout 120 python tools/prof_kernels.py --only fused --pairs-k 148 --utts 8 --C $c --iters 5 2>&1 | tail -1
+done; done | tee gpurun_out/ab_ns.log
+timeout 200 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "test_sim_stem_fused_matches_unfused_and_conv" 2>&1 | tail -2
+KWS_FUSED_NS=4 timeout 200 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "test_sim_stem_fused_matches_unfused_and_conv or channel_groups" 2>&1 | tail -2
