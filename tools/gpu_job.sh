@@ -1,5 +1,9 @@
-for c in 8 6; do for ns in 0 4 0 4; do
-  echo -n "C=$c NS=$ns: "; KWS_FUSED_NS=$ns timeout 120 python tools/prof_kernels.py --only fused --pairs-k 148 --utts 8 --C $c --iters 5 2>&1 | tail -1
-done; done | tee gpurun_out/ab_ns.log
-timeout 200 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "test_sim_stem_fused_matches_unfused_and_conv" 2>&1 | tail -2
-KWS_FUSED_NS=4 timeout 200 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "test_sim_stem_fused_matches_unfused_and_conv or channel_groups" 2>&1 | tail -2
+# round-end style validation on one B200: GPU tests, smoke, both bench arms (default flags)
+timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 400 python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; tail -1 gpurun_out/bench_full.err
+python -c "
+import json; d=json.load(open('gpurun_out/bench_full.json')); print(d['value'], d['e2e']['value'], d['e2e']['ms_per_step'], d['roofline']['frac'], d['cpu_baseline']['value'], d['cpu_baseline']['cores'], d['gpu_launches'], d['clocks'], d['wall_s'])"
+timeout 200 python tools/cfg4_bench.py --K 1000 --S 16 2>&1 | tail -1
+timeout 200 python bench.py --workload cfg1 --no-cpu --no-e2e > gpurun_out/bench_cfg1.json 2>/dev/null; python -c "
+import json; d=json.load(open('gpurun_out/bench_cfg1.json')); print('cfg1', round(d['value']), d['roofline']['frac'])"
