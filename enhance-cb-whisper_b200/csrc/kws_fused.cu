@@ -99,8 +99,7 @@ constexpr int G_TMEM_SIM = 2 * G_ACC_COLS;         // similarity region starts a
 constexpr int G_TMEM_BIAS = 448;                   // 64 columns: the folded-BN bias, replicated in every lane
 constexpr int G_OUT_STAGE = 4 * 32 * 128;          // per epilogue warp: 32 pixels x 64 bf16 (SW128), source of its TMA stores
 constexpr int G_NPAIR = G_MAX_C / 2;                 // similarity tiles are handed over per pair of layers
-constexpr int G_NS_MAX = 4;                        // ... when the stem weights leave room (<= 8 layers: 28 KB less)
-constexpr int G_NBAR = 2 * G_NS_MAX + 2 * G_NPAIR + 4 + 4 + 2 + 2 + 8;
+constexpr int G_NBAR = 2 * G_NS + 2 * G_NPAIR + 4 + 4 + 2 + 2 + 8;
 
 struct FusedParams {
   const uint4* w;     // fused stem weights (kws_pack_stem_fused)
@@ -120,7 +119,6 @@ struct FusedParams {
   int n_chunks;  // similarity chunks (ROWS input rows = ROWS/4 quanta) per item
   int w_bytes;   // bytes of this pass's stem weights in shared memory (7 * n_mma * 4096)
   int diag;
-  int ns;        // similarity operand stages
   int per_kw_u;  // KWS_PAIRS_PER_KEYWORD: utterance-side operand of pair (k, u) is bank item k * per_kw_u + u (else 0)
   int prefetch;  // multi-pass partial sums of step n+1: 1 = loaded into a second staging set during step n;
                  // 2 = pulled into L2 only (TMA prefetch), loaded and awaited in step n+1; 0 = neither
@@ -216,7 +214,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
   constexpr int G_STAGE = g_stage_bytes(ROWS);
   constexpr int NPAIR = 96 / ROWS;                // layer pairs the converters can hold: 6 / 3 / 2
   constexpr int QPC = ROWS / 4;                   // quanta per similarity chunk
-  const int NS = p.ns;                            // operand stages (3, or 4 where shared memory allows)
+  constexpr int NS = G_NS;                        // operand stages
   uint8_t* s_ops = base;                          // NS * G_STAGE (each 1024-aligned)
   uint8_t* s_w = s_ops + NS * G_STAGE;            // p.w_bytes (multiple of 4096)
   uint8_t* s_ostage = s_w + p.w_bytes;            // G_OUT_STAGE (4 x 4 KB, each 1024-aligned); two sets when MULTI
@@ -821,8 +819,8 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
   }
 }
 
-constexpr size_t g_smem_bytes(int rows, int n_mma, bool two_sets = false, int ns = G_NS) {
-  return (size_t)ns * g_stage_bytes(rows) + (size_t)7 * n_mma * G_MMA_W_BYTES +
+constexpr size_t g_smem_bytes(int rows, int n_mma, bool two_sets = false) {
+  return (size_t)G_NS * g_stage_bytes(rows) + (size_t)7 * n_mma * G_MMA_W_BYTES +
          (two_sets ? 2 : 1) * G_OUT_STAGE + G_RING_BYTES - 64 + G_NBAR * 8 + 16;
 }
 static_assert(g_smem_bytes(16, 3) <= 232448 && g_smem_bytes(32, 2) <= 232448 && g_smem_bytes(48, 2) <= 232448 &&
@@ -868,10 +866,6 @@ using namespace kws;
 static long long* g_fused_dbg = nullptr;
 static int g_fused_grid_limit = 0;
 static int g_fused_rows = 0;
-// A fourth operand stage where shared memory allows (<= 8 layers per pass, 16- or 32-row chunks): +1.4 % at 8 layers,
-// +2 % at 6 (same-box A/B) -- the similarity pipeline is bound by shared-memory port bandwidth, not by stages in flight.
-static int g_fused_ns = 4;  // KWS_FUSED_NS=3 / kws_debug_set_fused_stages(3) force three
-extern "C" void kws_debug_set_fused_stages(int ns) { g_fused_ns = ns; }
 // development aid: force the similarity chunk height (16 | 32 | 48) instead of choosing it from the layer count
 extern "C" void kws_debug_set_fused_rows(int rows) { g_fused_rows = rows; }
 // development aid: cap the number of CTAs (to separate per-SM limits from chip-wide L2 limits)
@@ -903,7 +897,6 @@ static void multi_cfg_from_env() {  // development aid: KWS_FUSED_MULTI="group,n
   static bool done = false;
   if (done) return;
   done = true;
-  if (const char* e = getenv("KWS_FUSED_NS")) g_fused_ns = atoi(e);
   if (const char* e = getenv("KWS_FUSED_MULTI")) {
     int g = 8, nh = 1, pf = 1, red = 1, sf = 1;
     const int n = sscanf(e, "%d,%d,%d,%d,%d", &g, &nh, &pf, &red, &sf);
@@ -1076,9 +1069,7 @@ extern "C" int kws_sim_stem_range(const void* kwd_n, const void* utt_n, int C, i
              : rows == 32 ? (nh ? kws_fused_kernel<true, 32, false> : kws_fused_kernel<false, 32, false>)
                           : (nh ? kws_fused_kernel<true, 16, false> : kws_fused_kernel<false, 16, false>);
     }
-    const bool two_sets = p.acc_mode != 0 && p.prefetch == 1;
-    p.ns = (g_fused_ns == 4 && g_smem_bytes(rows, p.n_mma, two_sets, 4) <= 232448) ? 4 : G_NS;
-    const size_t smem = g_smem_bytes(rows, p.n_mma, two_sets, p.ns);
+    const size_t smem = g_smem_bytes(rows, p.n_mma, p.acc_mode != 0 && p.prefetch == 1);
     KWS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     p.reduce_mid = g_multi_reduce;
     const bool red = p.acc_mode == 2 && p.reduce_mid;
