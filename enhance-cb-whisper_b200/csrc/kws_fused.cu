@@ -204,12 +204,18 @@ __device__ __forceinline__ ItemCoord decode_item(const FusedParams& p, long long
 // NHWC: bf16 channels-last through TMA stores; else fp32 NCHW with direct stores (parity).  ROWS: see above.
 // MULTI: channel-group passes (acc_mode 1..3) compiled in; single-pass launches use the leaner instance.
 // NHM: output channels / 16 per TMEM round trip of the multi-pass epilogue (1 | 2).
-template <bool NHWC, int ROWS, bool MULTI, int NHM = 2>
+// S12: the shape parameters of the 12-layer, Dk = 64 case (LE / LEF models: cfg2, the full groups of cfg3 / cfg5) are
+// compile-time constants -- the issuer loops are sensitive to every instruction (a run-time stage count cost 10 %).
+template <bool NHWC, int ROWS, bool MULTI, int NHM = 2, bool S12 = false>
 __global__ void __launch_bounds__(G_THREADS, 1)
 kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_constant__ CUtensorMap map_kwd,
                  const __grid_constant__ CUtensorMap map_out_lo, const __grid_constant__ CUtensorMap map_out_hi,
                  const FusedParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int kC = S12 ? 12 : p.C;                                  // layers of this pass
+  const int kNkb = S12 ? 1 : p.nkb;                               // 64-wide k-blocks per layer
+  const int kNmma = S12 ? 3 : p.n_mma;                            // stem MMAs per kernel row
+  const int kWbytes = S12 ? 7 * 3 * G_MMA_W_BYTES : p.w_bytes;    // stem weights in shared memory
   uint8_t* base = smem_raw;  // no alignment slack to spare: the declared 1024-byte alignment is checked below
   constexpr int G_STAGE = g_stage_bytes(ROWS);
   constexpr int NPAIR = 96 / ROWS;                // layer pairs the converters can hold: 6 / 3 / 2
@@ -217,7 +223,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
   constexpr int NS = G_NS;                        // operand stages
   uint8_t* s_ops = base;                          // NS * G_STAGE (each 1024-aligned)
   uint8_t* s_w = s_ops + NS * G_STAGE;            // p.w_bytes (multiple of 4096)
-  uint8_t* s_ostage = s_w + p.w_bytes;            // G_OUT_STAGE (4 x 4 KB, each 1024-aligned); two sets when MULTI
+  uint8_t* s_ostage = s_w + kWbytes;              // G_OUT_STAGE (4 x 4 KB, each 1024-aligned); two sets when MULTI
   uint8_t* s_ring = s_ostage + ((MULTI && p.prefetch == 1) ? 2 : 1) * G_OUT_STAGE;  // G_RING_BYTES
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + G_RING_BYTES - 64);  // from the last block's (unused) bank pad on
   uint64_t* ofull = bars;                 // [NS] TMA -> MMA (similarity operands)
@@ -235,7 +241,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
   const int lane = threadIdx.x & 31;
 
   {
-    const int w16 = 7 * p.n_mma * (G_MMA_W_BYTES / 16);
+    const int w16 = 7 * kNmma * (G_MMA_W_BYTES / 16);
     for (int i = threadIdx.x; i < w16; i += G_THREADS) reinterpret_cast<uint4*>(s_w)[i] = p.w[i];
     // the ring is zeroed once: chunks nobody writes (Y' of the last pixel, unused planes for C <= 8) must hold
     // finite values, they only ever meet zero weights or discarded pixel slots
@@ -287,7 +293,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
     if (threadIdx.x == 0) printf("[kws] unexpected TMEM base 0x%x\n", tmem_base);
     __trap();
   }
-  const int stages_per_chunk = p.C * p.nkb;
+  const int stages_per_chunk = kC * kNkb;
 
   if (warp == 0) {
     // ===================== TMA producer: similarity operands =====================
@@ -300,8 +306,8 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
         const int jbase = 2 * G_TILE_OJ * w.ct - 3;  // input column of pixel x = 0 (OOB columns read as zero)
         for (int n = 0; n < p.n_chunks; ++n) {
           if (ROWS * n - 3 >= p.Tk) continue;  // chunk entirely below the image (conv zero padding): nothing to load
-          for (int c = 0; c < p.C; ++c) {
-            for (int kb = 0; kb < p.nkb; ++kb) {
+          for (int c = 0; c < kC; ++c) {
+            for (int kb = 0; kb < kNkb; ++kb) {
               mbar_wait(&oempty[stage], phase ^ 1, 100 + stage);
               KWS_TRACE(3, tr_stage, 2);  // slot free seen by the producer
               uint8_t* sa = s_ops + stage * G_STAGE;
@@ -332,14 +338,14 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
           if (ROWS * n - 3 >= p.Tk) {
             // all-zero chunk: no operands, no MMAs; keep the tile hand-shake (the converters write zeros without
             // reading the tiles)
-            for (int j = 0; 2 * j < p.C; ++j) {
+            for (int j = 0; 2 * j < kC; ++j) {
               mbar_wait(&sempty[j], (g & 1) ^ 1, 500 + j);
               umma_commit(&sfull[j]);
             }
             continue;
           }
           for (int st = 0; st < stages_per_chunk; ++st) {
-            const int c = st / p.nkb, kb = st - c * p.nkb;
+            const int c = st / kNkb, kb = st - c * kNkb;
             // the converters have pulled the previous chunk's tiles of this layer pair out of TMEM
             if (st == 0) KWS_TRACE(2, g, 2);
             if (kb == 0 && (c & 1) == 0) mbar_wait(&sempty[c >> 1], (g & 1) ^ 1, 500 + (c >> 1));
@@ -360,7 +366,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
             ++tr_s;
             if (++o_stage == NS) o_stage = 0, o_phase ^= 1;
             // layer pair complete (or last layer of an odd C): hand its tiles to the converters
-            if (kb == p.nkb - 1 && ((c & 1) == 1 || c == p.C - 1)) umma_commit(&sfull[c >> 1]);
+            if (kb == kNkb - 1 && ((c & 1) == 1 || c == kC - 1)) umma_commit(&sfull[c >> 1]);
             if (st == stages_per_chunk - 1) KWS_TRACE(2, g, 5);
           }
         }
@@ -375,7 +381,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
       const uint64_t adesc_px = make_smem_desc(smem_u32(s_ring), 16, 128, LAYOUT_NONE);        // +1 pixel
       const uint64_t adesc_pl = make_smem_desc(smem_u32(s_ring), G_BLOCK, 128, LAYOUT_NONE);   // other plane
       const uint64_t bdesc0 = make_smem_desc(smem_u32(s_w), 128 * 16, 128, LAYOUT_NONE);
-      const int n_mma = p.n_mma;
+      const int n_mma = kNmma;
       uint32_t qbase = 0;    // global index of the current item's quantum 0
       uint32_t acc_seq = 0;  // global stem step counter -> accumulator buffer
       long long tm_acc = 0, tm_q = 0, tm_issue = 0;
@@ -708,7 +714,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
     uint8_t* dst_px = s_ring + (x & 1) * G_BLOCK + (x >> 1) * 16;
     const bool has_left = (x >> 1) > 0;  // Y' chunk of the left neighbour (same plane) takes our channels 8..11 too
     const uint32_t t_lane = tmem_base + G_TMEM_SIM + ((uint32_t)(q4 * 32) << 16);
-    const bool yp = p.n_mma == 3;
+    const bool yp = kNmma == 3;
     uint32_t g = 0;   // global similarity chunk counter
     uint32_t Gq = 0;  // global quantum counter
     long long tc_sfull = 0, tc_qempty = 0, tc_ld = 0, tc_st = 0;
@@ -723,19 +729,19 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
         uint32_t h2[ROWS][NPAIR];  // [row][layer pair] fp16x2
 #pragma unroll
         for (int j = 0; j < NPAIR; ++j) {
-          if (2 * j < p.C && 4 * q0 - 3 >= p.Tk) {  // chunk entirely below the image: zeros, tiles untouched
+          if (2 * j < kC && 4 * q0 - 3 >= p.Tk) {  // chunk entirely below the image: zeros, tiles untouched
             mbar_wait(&sfull[j], g & 1, 700 + j);
             mbar_arrive(&sempty[j]);
 #pragma unroll
             for (int r = 0; r < ROWS; ++r) h2[r][j] = 0u;
-          } else if (2 * j < p.C) {
+          } else if (2 * j < kC) {
             mbar_wait(&sfull[j], g & 1, 700 + j);
             tc_fence_after();
 #pragma unroll
             for (int b = 0; b < ROWS / 16; ++b) {  // 16 rows x 2 layers per TMEM round trip (32 transient registers)
               uint32_t v0[16], v1[16];
               tmem_ld16(t_lane + (2 * j) * ROWS + 16 * b, v0);
-              if (2 * j + 1 < p.C) {
+              if (2 * j + 1 < kC) {
                 tmem_ld16(t_lane + (2 * j + 1) * ROWS + 16 * b, v1);
               } else {
 #pragma unroll
@@ -866,6 +872,8 @@ using namespace kws;
 static long long* g_fused_dbg = nullptr;
 static int g_fused_grid_limit = 0;
 static int g_fused_rows = 0;
+static int g_fused_s12 = 1;  // use the 12-layer / Dk = 64 specialisation (development aid: KWS_FUSED_S12=0 turns it off)
+extern "C" void kws_debug_set_fused_s12(int on) { g_fused_s12 = on ? 1 : 0; }
 // development aid: force the similarity chunk height (16 | 32 | 48) instead of choosing it from the layer count
 extern "C" void kws_debug_set_fused_rows(int rows) { g_fused_rows = rows; }
 // development aid: cap the number of CTAs (to separate per-SM limits from chip-wide L2 limits)
@@ -897,6 +905,7 @@ static void multi_cfg_from_env() {  // development aid: KWS_FUSED_MULTI="group,n
   static bool done = false;
   if (done) return;
   done = true;
+  if (const char* e = getenv("KWS_FUSED_S12")) g_fused_s12 = atoi(e);
   if (const char* e = getenv("KWS_FUSED_MULTI")) {
     int g = 8, nh = 1, pf = 1, red = 1, sf = 1;
     const int n = sscanf(e, "%d,%d,%d,%d,%d", &g, &nh, &pf, &red, &sf);
@@ -1062,12 +1071,14 @@ extern "C" int kws_sim_stem_range(const void* kwd_n, const void* utt_n, int C, i
     void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, FusedParams);
     if (p.acc_mode != 0) {
       kern = g_multi_nh == 1 ? kws_fused_kernel<true, 16, true, 1> : kws_fused_kernel<true, 16, true, 2>;
+      if (g_multi_nh != 1 && Cg == 12 && p.nkb == 1 && g_fused_s12) kern = kws_fused_kernel<true, 16, true, 2, true>;
       p.prefetch = g_multi_prefetch;
       KWS_CHECK_ARG(rows == 16 && nh, "sim_stem: internal: multi-pass needs 16-row chunks, bf16 output");
     } else {
       kern = rows == 48 ? (nh ? kws_fused_kernel<true, 48, false> : kws_fused_kernel<false, 48, false>)
              : rows == 32 ? (nh ? kws_fused_kernel<true, 32, false> : kws_fused_kernel<false, 32, false>)
                           : (nh ? kws_fused_kernel<true, 16, false> : kws_fused_kernel<false, 16, false>);
+      if (rows == 16 && nh && Cg == 12 && p.nkb == 1 && g_fused_s12) kern = kws_fused_kernel<true, 16, false, 2, true>;
     }
     const size_t smem = g_smem_bytes(rows, p.n_mma, p.acc_mode != 0 && p.prefetch == 1);
     KWS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
