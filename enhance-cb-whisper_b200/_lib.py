@@ -11,8 +11,9 @@ import os
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libkws_b200.so")
-ABI_VERSION = 6
+# KWS_B200_LIB: explicit path of another flavour of the same ABI (the -DKWS_DEBUG_HOOKS development build)
+LIB_PATH = os.environ.get("KWS_B200_LIB") or os.path.join(HERE, "libkws_b200.so")
+ABI_VERSION = 7
 
 # constants of include/kws_b200.h
 F16, BF16 = 0, 1
@@ -49,7 +50,8 @@ SIGNATURES = {
     "kws_resize_row_weights": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "kws_maxpool_nhwc": (_i, [_vp, C.c_longlong, _i, _i, _i, _vp, _vp]),
     "kws_scores": (_i, [_vp, _vp, _sz, _f, _vp, _vp, _vp]),
-    "kws_topk": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "kws_topk": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "kws_topk_workspace_bytes": (_sz, [_i, _i, _i]),
 }
 
 

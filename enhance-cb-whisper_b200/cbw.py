@@ -39,10 +39,15 @@ from .model import run_body
 FUSED_MAX_FRAMES = 64  # keyword frames the fused path holds as the contraction dimension of the height map
 
 
+NO_NORM = -1.0  # eps < 0 for kws_normalize_rows / kws_interp_rows: hidden states are used as given
+
+
 def pack_keywords(kwd_list: Sequence[torch.Tensor], device: torch.device, multiple: int = 16):
     """Ragged pre-normalised keywords [C, Tk_i, D] -> (fp16 operand bank [C, K, Tkp, D], int32 lengths [K]).
     Rows beyond a keyword's length are zero (they produce zero similarity and are never sampled by the
-    resize)."""
+    resize).  Like the reference (plain ``torch.matmul`` on whatever it is given, cb_whisper.py:197) the states
+    are NOT re-normalised: the caller normalises them once (cb_whisper.py:106, src/utils.py:195).  Operands are
+    fp16: states far outside [-1, 1] lose precision, unit vectors keep the similarity within ~3e-4."""
     if len(kwd_list) == 0:
         raise ops.KWSError("empty keyword list")
     C, _, D = kwd_list[0].shape
@@ -55,9 +60,8 @@ def pack_keywords(kwd_list: Sequence[torch.Tensor], device: torch.device, multip
         if k.shape[0] != C or k.shape[2] != D:
             raise ops.KWSError(f"keyword {i} has shape {tuple(k.shape)}, expected [{C}, T, {D}]")
         bank[i, :, : lens[i]] = k.to(device=device, dtype=torch.float32)
-    # operands are already unit vectors (src/utils.py:195); normalize_rows re-normalises (a no-op up to
-    # rounding), zeroes nothing (mask None) and casts to the layer-major fp16 layout
-    kwd_n = ops.normalize_rows(bank, list(range(C)), None)
+    # layer-major fp16 layout, values as given (eps < 0: no normalisation)
+    kwd_n = ops.normalize_rows(bank, list(range(C)), None, eps=NO_NORM)
     return kwd_n, torch.tensor(lens, dtype=torch.int32, device=device)
 
 
@@ -73,7 +77,7 @@ def similarity_images(kwd_list: Sequence[torch.Tensor], utt_hs: torch.Tensor, si
     dev = utt_hs.device
     S, C, Tu, D = utt_hs.shape
     kwd_n, lens = pack_keywords(kwd_list, dev)
-    utt_n = ops.normalize_rows(utt_hs.float().contiguous(), list(range(C)), None)
+    utt_n = ops.normalize_rows(utt_hs.float().contiguous(), list(range(C)), None, eps=NO_NORM)
     K = kwd_n.shape[1]
     # bound the fp32 intermediate [kb, S, C, Tkp, Tu]
     per_kw = S * C * kwd_n.shape[2] * Tu * 4
@@ -170,7 +174,7 @@ class CBWKeywordSpotterB200:
                 raise ops.KWSError("fused config-#4 path needs keywords <= 64 frames, D % 64 == 0, D <= 1280")
             S, C = utt_hs.shape[0], utt_hs.shape[1]
             kwd_n, lens = pack_keywords(kwd_list, dev, multiple=FUSED_MAX_FRAMES)
-            utt_i = ops.interp_rows(utt_hs.float().contiguous(), list(range(C)), self.size[1])
+            utt_i = ops.interp_rows(utt_hs.float().contiguous(), list(range(C)), self.size[1], eps=NO_NORM)
             K = kwd_n.shape[1]
             out = torch.empty((K, S, 2), dtype=torch.float32, device=dev)
 
@@ -189,6 +193,32 @@ class CBWKeywordSpotterB200:
             st = ops.stem(flat[p0:p1], self.size[1], wp, bias, out_mode)
             out[p0:p1] = self._body(st).float()
         return out.view(K, S, 2)
+
+    @torch.no_grad()
+    def keyword_spotting(self, utt_hs: Optional[torch.Tensor], kw_groups, n_segments: Optional[int] = None,
+                         max_pairs: int = 128) -> List[List[str]]:
+        """The ``oracle == 'kws'`` branch of ``CBWhisper.keyword_spotting`` (src/model/cb_whisper.py:96-131) with
+        the similarity / resize / classifier on the B200 path.
+
+        utt_hs: [S, C, Tu, D] normalised encoder hidden states of the S segments (cb_whisper.py:100-106), or None
+        when feature extraction failed (every segment then retrieves nothing, :113-116).  kw_groups: iterable of
+        keyword-database groups, each a mapping with ``'hidden_states'`` (list of [C, Tk_i, D]) and ``'keywords'``
+        (list of str) -- what ``kw_database.group(idx)`` returns.  Returns, per segment, the de-duplicated
+        retrieved keywords (``argmax(logits) == 1``, :126-131); order within a segment is unspecified, as in the
+        reference (``list(set(...))``)."""
+        S = utt_hs.shape[0] if utt_hs is not None else int(n_segments or 1)
+        keywords: List[List[str]] = [[] for _ in range(S)]
+        if utt_hs is None:
+            return keywords
+        for group in kw_groups:
+            hs = group["hidden_states"]
+            if len(hs) == 0:
+                continue
+            hit = self.logits(hs, utt_hs, max_pairs=max_pairs).argmax(dim=-1) == 1  # [K,S]
+            hit = hit.cpu()
+            for s in range(S):
+                keywords[s] += [group["keywords"][i] for i in torch.nonzero(hit[:, s]).flatten().tolist()]
+        return [list(set(k)) for k in keywords]
 
     @torch.no_grad()
     def detect(self, kwd_list: Sequence[torch.Tensor], utt_hs: torch.Tensor) -> List[List[int]]:

@@ -869,39 +869,54 @@ __global__ void pack_stem_fused_kernel(const float* __restrict__ w, const float*
 
 using namespace kws;
 
+// Development hooks (cycle counters, forced chunk heights, multi-pass variants) exist only in the -DKWS_DEBUG_HOOKS
+// flavour of the library (build.py --debug-hooks -> libkws_b200_dbg.so, used by tools/ and by the variant tests).
+// The release library has NO mutable global state here: every knob below is a compile-time constant, no getenv,
+// no exported setter, so weights packed by one call can never meet a kernel configured by another.
+#ifdef KWS_DEBUG_HOOKS
+#define KWS_KNOB static int
+#else
+#define KWS_KNOB static constexpr int
+#endif
+#ifdef KWS_DEBUG_HOOKS
 static long long* g_fused_dbg = nullptr;
-static int g_fused_grid_limit = 0;
-static int g_fused_rows = 0;
-static int g_fused_s12 = 1;  // use the 12-layer / Dk = 64 specialisation (development aid: KWS_FUSED_S12=0 turns it off)
-extern "C" void kws_debug_set_fused_s12(int on) { g_fused_s12 = on ? 1 : 0; }
-// development aid: force the similarity chunk height (16 | 32 | 48) instead of choosing it from the layer count
-extern "C" void kws_debug_set_fused_rows(int rows) { g_fused_rows = rows; }
-// development aid: cap the number of CTAs (to separate per-SM limits from chip-wide L2 limits)
-extern "C" void kws_debug_set_fused_grid_limit(int n) { g_fused_grid_limit = n; }
-
-// development aid (not part of the public header): device buffer [148][8] receiving the issuer's cycle counters
-extern "C" void kws_debug_set_fused_counters(long long* dev_buf) { g_fused_dbg = dev_buf; }
-
+#else
+static constexpr long long* g_fused_dbg = nullptr;
+#endif
+KWS_KNOB g_fused_grid_limit = 0;
+KWS_KNOB g_fused_rows = 0;
+KWS_KNOB g_fused_s12 = 1;  // 12-layer / Dk = 64 compile-time specialisation
 static int fused_n_mma(int C) { return C <= 8 ? 2 : 3; }
 // C > 12 layers are processed in passes over channel groups of 12 layers; the passes chain their
 // partial sums through the output buffer itself (fp16, same tiles), the last one adds bias + ReLU -> bf16.
 constexpr int G_MAX_C_TOTAL = 64;
-static int g_multi_group = 12, g_multi_nh = 2, g_multi_prefetch = 2, g_multi_reduce = 1;
-extern "C" void kws_debug_set_fused_reduce(int on) { g_multi_reduce = on ? 1 : 0; }
-static int g_multi_small_first = 0;
-extern "C" void kws_debug_set_fused_small_first(int on) { g_multi_small_first = on ? 1 : 0; }
-// Multi-pass variants (development aid; measured at the cfg3 slab, pairs/s): layers per pass 12 | 8, output
-// channels / 16 per epilogue TMEM round trip 2 | 1, partial-sum prefetch 0 none | 1 into a second staging set
-// (8-layer groups only: their smaller weights leave the 16 KB free) | 2 into L2 only.
-//   12,2,2: 185 k (default)   12,2,0: 178 k   12,1,0: 162 k   8,2,1: 157 k   8,2,2: 149 k   8,1,1: 143 k   8,2,0: 135 k
+// Multi-pass variants (measured at the cfg3 slab, pairs/s): layers per pass 12 | 8, output channels / 16 per epilogue
+// TMEM round trip 2 | 1, partial-sum prefetch 0 none | 1 into a second staging set (8-layer groups only) | 2 into L2 only.
+//   12,2,2: 185 k (shipped)   12,2,0: 178 k   12,1,0: 162 k   8,2,1: 157 k   8,2,2: 149 k   8,1,1: 143 k   8,2,0: 135 k
 // The multi-pass epilogue (TMA load + add of the previous partial sums) is what bounds these shapes: the stem issuer
 // waits for accumulators, so fewer, fatter passes win even though the 2-trip epilogue spills 8 registers.
+KWS_KNOB g_multi_group = 12;
+KWS_KNOB g_multi_nh = 2;
+KWS_KNOB g_multi_prefetch = 2;
+KWS_KNOB g_multi_reduce = 1;       // middle passes: TMA reduce-add store (1) | load + add + store (0)
+KWS_KNOB g_multi_small_first = 0;  // remainder group first (no measurable difference; kept as a variant)
+#ifdef KWS_DEBUG_HOOKS
+extern "C" void kws_debug_set_fused_s12(int on) { g_fused_s12 = on ? 1 : 0; }
+// force the similarity chunk height (16 | 32 | 48) instead of choosing it from the layer count
+extern "C" void kws_debug_set_fused_rows(int rows) { g_fused_rows = rows; }
+// cap the number of CTAs (to separate per-SM limits from chip-wide L2 limits)
+extern "C" void kws_debug_set_fused_grid_limit(int n) { g_fused_grid_limit = n; }
+// device buffer [148][32] receiving the roles' cycle counters (needs -DKWS_FUSED_TIMERS as well)
+extern "C" void kws_debug_set_fused_counters(long long* dev_buf) { g_fused_dbg = dev_buf; }
+extern "C" void kws_debug_set_fused_reduce(int on) { g_multi_reduce = on ? 1 : 0; }
+extern "C" void kws_debug_set_fused_small_first(int on) { g_multi_small_first = on ? 1 : 0; }
+// NOTE: weights must be re-packed (kws_pack_stem_fused) after changing the group size or order.
 extern "C" void kws_debug_set_fused_multi(int group, int nh, int prefetch) {
   g_multi_group = group == 12 ? 12 : 8;
   g_multi_nh = nh == 2 ? 2 : 1;
   g_multi_prefetch = prefetch == 2 ? 2 : ((prefetch == 1 && g_multi_group == 8) ? 1 : 0);
 }
-static void multi_cfg_from_env() {  // development aid: KWS_FUSED_MULTI="group,nh,prefetch", read once
+static void multi_cfg_from_env() {  // KWS_FUSED_MULTI="group,nh,prefetch[,reduce[,small_first]]", KWS_FUSED_S12, read once
   static bool done = false;
   if (done) return;
   done = true;
@@ -914,6 +929,9 @@ static void multi_cfg_from_env() {  // development aid: KWS_FUSED_MULTI="group,n
     if (n >= 5) kws_debug_set_fused_small_first(sf);
   }
 }
+#else
+static inline void multi_cfg_from_env() {}
+#endif
 static int fused_group_size(int C) {
   multi_cfg_from_env();
   return C <= G_MAX_C ? G_MAX_C : g_multi_group;
@@ -1070,7 +1088,10 @@ extern "C" int kws_sim_stem_range(const void* kwd_n, const void* utt_n, int C, i
     const bool nh = out_mode == KWS_STEM_OUT_NHWC_BF16;
     void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, FusedParams);
     if (p.acc_mode != 0) {
-      kern = g_multi_nh == 1 ? kws_fused_kernel<true, 16, true, 1> : kws_fused_kernel<true, 16, true, 2>;
+      kern = kws_fused_kernel<true, 16, true, 2>;
+#ifdef KWS_DEBUG_HOOKS
+      if (g_multi_nh == 1) kern = kws_fused_kernel<true, 16, true, 1>;
+#endif
       if (g_multi_nh != 1 && Cg == 12 && p.nkb == 1 && g_fused_s12) kern = kws_fused_kernel<true, 16, true, 2, true>;
       p.prefetch = g_multi_prefetch;
       KWS_CHECK_ARG(rows == 16 && nh, "sim_stem: internal: multi-pass needs 16-row chunks, bf16 output");

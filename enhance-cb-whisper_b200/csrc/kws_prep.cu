@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256) rows_kernel(const float* __restrict__ x, 
     if (NORMALIZE) {
       ss = warp_sum(ss);
       const float m = mask ? mask[((long long)b * C + c) * T + t] : 1.f;
-      scale = m / fmaxf(sqrtf(ss), eps);
+      scale = eps < 0.f ? m : m / fmaxf(sqrtf(ss), eps);  // eps < 0: rows are used as given (mask + cast only)
     }
     uint2* dst = reinterpret_cast<uint2*>(out + row * D);
 #pragma unroll
@@ -230,7 +230,9 @@ __global__ void __launch_bounds__(256) interp_rows_kernel(const float* __restric
         ssq += q[i].x * q[i].x + q[i].y * q[i].y + q[i].z * q[i].z + q[i].w * q[i].w;
       }
     }
-    const float ka = w0 / fmaxf(sqrtf(warp_sum(ssa)), eps), kq = w1 / fmaxf(sqrtf(warp_sum(ssq)), eps);
+    // eps < 0: frames are used as given (the reference's plain matmul on pre-normalised states, cb_whisper.py:197)
+    const float ka = eps < 0.f ? w0 : w0 / fmaxf(sqrtf(warp_sum(ssa)), eps);
+    const float kq = eps < 0.f ? w1 : w1 / fmaxf(sqrtf(warp_sum(ssq)), eps);
     uint2* dst = reinterpret_cast<uint2*>(out + row * D);
 #pragma unroll
     for (int i = 0; i < IR_MAX_V4; ++i) {
@@ -284,51 +286,75 @@ __global__ void scores_kernel(const float* __restrict__ logits, const float* __r
   }
 }
 
-// one block per utterance; k rounds of block-wide arg-max over the candidates
-// (k is small: the reference uses recall@{1..200}); ties -> lower id first.
-__global__ void __launch_bounds__(256) topk_kernel(const float* __restrict__ scores, const int32_t* __restrict__ ids,
-                                                   int n, int U, int id_offset, int k, float* __restrict__ os,
-                                                   int32_t* __restrict__ oi) {
-  extern __shared__ unsigned long long s_taken[];  // bitmap of taken candidates
-  __shared__ float s_best[8];
-  __shared__ int s_bid[8], s_bpos[8];
-  const int u = blockIdx.x, tid = threadIdx.x;
-  const int words = (n + 63) / 64;
-  for (int i = tid; i < words; i += blockDim.x) s_taken[i] = 0ull;
+// Per-utterance top-k over the keyword axis (replaces torch.topk, model.py:523), any n_cand, k <= 1024.
+// Candidates are ordered by one 64-bit key, (orderable(score) << 32) | (0xffffffff - id): larger key = higher score,
+// lower id on equal scores -- so a sharded top-k followed by a merge gives exactly the single-device result.
+// A block sorts one SEGMENT of TK_SEG candidates for TK_UG neighbouring utterances in shared memory (bitonic,
+// descending) and keeps the first k keys of each; the survivors of all segments (n' = segments * k) go through the
+// same kernel again until one segment is left.  Every level reads its input once, TK_UG neighbouring utterances per
+// candidate row (the old kernel walked the whole strided column k times: ~10^10 uncoalesced loads at 100 k x 512, k = 200).
+constexpr int TK_SEG = 2048;
+constexpr int TK_UG = 4;
+constexpr int TK_THREADS = 512;
+
+__device__ __forceinline__ uint32_t f32_orderable(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float f32_from_orderable(uint32_t o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+// in: scores/ids (level 0) or keys_in (later levels), n candidates x U; this block: segment blockIdx.x, utterances
+// [TK_UG * blockIdx.y, +TK_UG).  out: keys_out [gridDim.x * k, U], or (final) out_scores/out_ids [k, U].
+__global__ void __launch_bounds__(TK_THREADS) topk_segment_kernel(const float* __restrict__ scores, const int32_t* __restrict__ ids,
+                                                                  const unsigned long long* __restrict__ keys_in, int n, int U,
+                                                                  int id_offset, int k, unsigned long long* __restrict__ keys_out,
+                                                                  float* __restrict__ os, int32_t* __restrict__ oi) {
+  extern __shared__ unsigned long long s_keys[];  // [TK_UG][TK_SEG]
+  const int c0 = blockIdx.x * TK_SEG, u0 = blockIdx.y * TK_UG;
+  for (int i = threadIdx.x; i < TK_SEG * TK_UG; i += TK_THREADS) {
+    const int c = i / TK_UG, uu = i % TK_UG;
+    unsigned long long key = 0ull;  // padding: below every real candidate
+    if (c0 + c < n && u0 + uu < U) {
+      const size_t g = (size_t)(c0 + c) * U + u0 + uu;
+      if (keys_in) {
+        key = keys_in[g];
+      } else {
+        const uint32_t id = ids ? (uint32_t)ids[g] : (uint32_t)(id_offset + c0 + c);
+        key = ((unsigned long long)f32_orderable(scores[g]) << 32) | (unsigned long long)(0xffffffffu - id);
+        if (key == 0ull) key = 1ull;  // (-NaN, id 0xffffffff) cannot occur with int32 ids; keep 0 for padding only
+      }
+    }
+    s_keys[uu * TK_SEG + c] = key;
+  }
   __syncthreads();
-  for (int r = 0; r < k; ++r) {
-    float best = -INFINITY;
-    int bid = 0x7fffffff, bpos = -1;
-    for (int c = tid; c < n; c += blockDim.x) {
-      if ((s_taken[c >> 6] >> (c & 63)) & 1ull) continue;
-      const float v = scores[(size_t)c * U + u];
-      const int id = ids ? ids[(size_t)c * U + u] : id_offset + c;
-      if (bpos < 0 || v > best || (v == best && id < bid)) best = v, bid = id, bpos = c;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oid = __shfl_xor_sync(0xffffffffu, bid, o);
-      const int op = __shfl_xor_sync(0xffffffffu, bpos, o);
-      if (op >= 0 && (bpos < 0 || ov > best || (ov == best && oid < bid))) best = ov, bid = oid, bpos = op;
-    }
-    if ((tid & 31) == 0) s_best[tid >> 5] = best, s_bid[tid >> 5] = bid, s_bpos[tid >> 5] = bpos;
-    __syncthreads();
-    if (tid == 0) {
-      for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
-        if (s_bpos[w] >= 0 && (bpos < 0 || s_best[w] > best || (s_best[w] == best && s_bid[w] < bid)))
-          best = s_best[w], bid = s_bid[w], bpos = s_bpos[w];
+  for (int size = 2; size <= TK_SEG; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int p = threadIdx.x; p < TK_UG * (TK_SEG / 2); p += TK_THREADS) {
+        const int uu = p / (TK_SEG / 2), q = p % (TK_SEG / 2);
+        const int i = ((q / stride) * 2 * stride) + (q % stride), j = i + stride;
+        unsigned long long* a = s_keys + uu * TK_SEG;
+        const unsigned long long x = a[i], y = a[j];
+        const bool desc = (i & size) == 0;  // final merge (size == TK_SEG): descending everywhere
+        if ((x < y) == desc) a[i] = y, a[j] = x;
       }
-      if (bpos >= 0) {
-        s_taken[bpos >> 6] |= 1ull << (bpos & 63);
-        os[(size_t)r * U + u] = best;
-        oi[(size_t)r * U + u] = bid;
-      } else {  // fewer candidates than k
-        os[(size_t)r * U + u] = -INFINITY;
-        oi[(size_t)r * U + u] = -1;
-      }
+      __syncthreads();
     }
-    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < k * TK_UG; i += TK_THREADS) {
+    const int r = i / TK_UG, uu = i % TK_UG;
+    if (u0 + uu >= U) continue;
+    const unsigned long long key = r < TK_SEG ? s_keys[uu * TK_SEG + r] : 0ull;
+    if (keys_out) {
+      keys_out[((size_t)blockIdx.x * k + r) * U + u0 + uu] = key;
+    } else if (key == 0ull) {  // fewer candidates than k
+      os[(size_t)r * U + u0 + uu] = -INFINITY;
+      oi[(size_t)r * U + u0 + uu] = -1;
+    } else {
+      os[(size_t)r * U + u0 + uu] = f32_from_orderable((uint32_t)(key >> 32));
+      oi[(size_t)r * U + u0 + uu] = (int32_t)(0xffffffffu - (uint32_t)key);
+    }
   }
 }
 
@@ -508,14 +534,45 @@ int kws_scores(const float* logits, const float* hotword_mask, size_t n, float t
   return 0;
 }
 
+size_t kws_topk_workspace_bytes(int n_cand, int U, int k) {
+  if (n_cand <= TK_SEG || U <= 0 || k <= 0) return 0;
+  // level-1 survivors + level-2 survivors (ping-pong); later levels are smaller and reuse the two halves
+  const size_t s0 = (size_t)((n_cand + TK_SEG - 1) / TK_SEG), n1 = s0 * (size_t)k;
+  const size_t s1 = (n1 + TK_SEG - 1) / TK_SEG;
+  return (n1 + s1 * (size_t)k) * (size_t)U * sizeof(unsigned long long);
+}
+
 int kws_topk(const float* scores, const int32_t* ids, int n_cand, int U, int id_offset, int k, float* out_scores,
-             int32_t* out_ids, void* stream) {
+             int32_t* out_ids, void* workspace, void* stream) {
   KWS_CHECK_ARG(scores && out_scores && out_ids, "topk: null pointer");
   KWS_CHECK_ARG(n_cand > 0 && U > 0 && k > 0 && k <= 1024, "topk: need n_cand>0, U>0, 0<k<=1024");
-  const size_t smem = (size_t)((n_cand + 63) / 64) * sizeof(unsigned long long);
-  KWS_CHECK_ARG(smem <= 48 * 1024, "topk: n_cand=%d too large for one pass (max %d)", n_cand, 48 * 1024 * 8);
-  topk_kernel<<<U, 256, smem, (cudaStream_t)stream>>>(scores, ids, n_cand, U, id_offset, k, out_scores, out_ids);
-  KWS_CUDA(cudaGetLastError());
+  KWS_CHECK_ARG(n_cand <= TK_SEG || workspace, "topk: n_cand=%d > %d needs a workspace of kws_topk_workspace_bytes()",
+                n_cand, TK_SEG);
+  KWS_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 7) == 0, "topk: workspace must be 8-byte aligned");
+  const size_t smem = (size_t)TK_UG * TK_SEG * sizeof(unsigned long long);
+  KWS_CUDA(cudaFuncSetAttribute(topk_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const unsigned ugroups = (unsigned)((U + TK_UG - 1) / TK_UG);
+  KWS_CHECK_ARG(ugroups <= 65535, "topk: U=%d too large", U);
+  unsigned long long* buf[2];
+  {
+    const size_t s0 = (size_t)((n_cand + TK_SEG - 1) / TK_SEG);
+    buf[0] = reinterpret_cast<unsigned long long*>(workspace);
+    buf[1] = buf[0] ? buf[0] + s0 * (size_t)k * (size_t)U : nullptr;
+  }
+  const unsigned long long* keys_in = nullptr;
+  long long n = n_cand;
+  for (int level = 0;; ++level) {
+    const long long segs = (n + TK_SEG - 1) / TK_SEG;
+    const bool last = segs == 1;
+    unsigned long long* keys_out = last ? nullptr : buf[level & 1];
+    topk_segment_kernel<<<dim3((unsigned)segs, ugroups), TK_THREADS, smem, (cudaStream_t)stream>>>(
+        level == 0 ? scores : nullptr, level == 0 ? ids : nullptr, keys_in, (int)n, U, id_offset, k, keys_out,
+        out_scores, out_ids);
+    KWS_CUDA(cudaGetLastError());
+    if (last) break;
+    keys_in = keys_out;
+    n = segs * k;
+  }
   return 0;
 }
 

@@ -106,6 +106,11 @@ class KWSEngine:
         if x.dtype != torch.float32:
             x = x.float()
         if mask is not None:
+            want = (B, w.C, self.out_frames(T))
+            if tuple(mask.shape) != want:
+                # e.g. the [B,12,T] masks of the eval datasets without the [-n_layers:] slice, or a full-resolution
+                # mask for LEF: the kernels index mask[(b*C + c)*T' + t], so a wrong shape must not get through
+                raise ops.KWSError(f"mask must be [B,C,T']={want} for the {w.variant} variant, got {tuple(mask.shape)}")
             mask = mask.to(torch.float32).contiguous()
         if w.variant == "L":
             return ops.normalize_rows(x, layer_idx, mask)

@@ -8,8 +8,14 @@ Switch one line of any ``src/efficient_kws/configs/*.yaml``::
       class_path: enhance_cb_whisper_b200.lightning.KWSModelB200
 
 ``run_efficient_kws.py`` (``subclass_mode_model=True``, :50) instantiates it with
-the unchanged ``init_args``; ``test_step`` / ``validation_step`` and every
-metric hook are inherited from the reference, only ``forward`` is replaced.
+the unchanged ``init_args``.  Replaced: ``forward`` (B200 kernels) and, in eval
+mode, ``test_step`` / ``validation_step`` (model.py:748-802, :304-385): all keyword
+groups of a DataLoader item are stacked and scored in ONE pass, so the utterance is
+compressed once instead of once per group of 50 keywords; what they append to
+``test_step_outputs`` / ``validation_step_outputs`` is unchanged.  Every other hook
+(epoch-end metrics, ``on_load_checkpoint`` legacy remap, optimisers, ``training_step``)
+is inherited from the reference.  Covered by tests/test_lightning.py under the stub
+modules of oracle/ref_stub.
 Optional extra init args: ``b200_body_dtype`` ("float32" | "bfloat16"),
 ``b200_return_features`` (bool), ``b200_layer_idx`` (list of int), ``b200_mlp_dtype``
 ("float16" | "bfloat16").

@@ -38,6 +38,30 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def _guard(fn):
+    """Run an op on the device of its first CUDA tensor argument: the library launches on the CURRENT device and
+    ``_stream()`` is that device's current stream, so tensors living on another GPU would otherwise be handed to
+    kernels on the wrong device/stream."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        dev = None
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                dev = a.device
+                break
+        if dev is None and isinstance(kwargs.get("device"), (torch.device, str)):
+            d = torch.device(kwargs["device"])
+            dev = d if d.type == "cuda" else None
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+
+    return wrapped
+
+
 # kernels launched through this module since import (bench.py reports the count of the timed region)
 LAUNCHES = 0
 _KERNELS_PER_CALL = {"kws_mlp": 2}
@@ -59,6 +83,7 @@ def sm_count() -> int:
 
 
 # ---- once per checkpoint -----------------------------------------------------
+@_guard
 def pack_stem_weights(conv_w, gamma, beta, mean, var, eps: float = BN_EPS) -> Tuple[torch.Tensor, torch.Tensor]:
     """-> (w_packed fp16 [G,49,2,64,8], bias fp32 [64])"""
     lib = _lib.load()
@@ -74,6 +99,7 @@ def pack_stem_weights(conv_w, gamma, beta, mean, var, eps: float = BN_EPS) -> Tu
     return wp, bias
 
 
+@_guard
 def pack_stem_fused(conv_w, gamma, beta, mean, var, eps: float = BN_EPS) -> Tuple[torch.Tensor, torch.Tensor]:
     """Stem conv + BN folded and packed for the fused similarity+stem kernel
     -> (w_fused fp16 [kws_stem_fused_weight_bytes(C) / 2], bias fp32 [64]); C <= 12."""
@@ -92,6 +118,7 @@ def pack_stem_fused(conv_w, gamma, beta, mean, var, eps: float = BN_EPS) -> Tupl
     return wf, bias
 
 
+@_guard
 def fold_temporal_weights(conv_w, conv_b, gamma, beta, mean, var, eps: float = BN_EPS, dtype16: int = F16):
     """conv_w [C,P,P,3] ... -> (w16 packed fp16|bf16 [C,3,P/8,P,8], b_folded fp32 [C,P])"""
     lib = _lib.load()
@@ -105,6 +132,7 @@ def fold_temporal_weights(conv_w, conv_b, gamma, beta, mean, var, eps: float = B
     return wf, bf
 
 
+@_guard
 def cast16(src: torch.Tensor, dtype16: int = F16) -> torch.Tensor:
     """fp32 -> fp16 (saturating) | bf16"""
     lib = _lib.load()
@@ -116,6 +144,7 @@ def cast16(src: torch.Tensor, dtype16: int = F16) -> torch.Tensor:
 
 
 # ---- per batch of keywords / utterances ----------------------------------------
+@_guard
 def normalize_rows(x: torch.Tensor, layer_idx: Sequence[int], mask: Optional[torch.Tensor],
                    eps: float = SIM_EPS) -> torch.Tensor:
     """x fp32 [B,Cin,T,D] -> fp16 [C,B,T,D] (selected layers, L2-normalised, mask folded)."""
@@ -131,6 +160,7 @@ def normalize_rows(x: torch.Tensor, layer_idx: Sequence[int], mask: Optional[tor
     return out
 
 
+@_guard
 def cast_rows16(x: torch.Tensor, layer_idx: Sequence[int], dtype16: int = F16) -> torch.Tensor:
     """x fp32 [B,Cin,T,D] -> fp16|bf16 [C, B*T, D] (selected layers, layer-major rows)."""
     lib = _lib.load()
@@ -142,6 +172,7 @@ def cast_rows16(x: torch.Tensor, layer_idx: Sequence[int], dtype16: int = F16) -
     return out
 
 
+@_guard
 def mlp(x16: torch.Tensor, B: int, T: int, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor,
         b2: torch.Tensor, mask: Optional[torch.Tensor], out_mode: int, eps: float = SIM_EPS) -> torch.Tensor:
     """x [C,B*T,D]; w1 [C,H,D]; w2 [C,P,H] all fp16 or all bf16; b1 fp32 [C,H]; b2 fp32 [C,P]
@@ -158,6 +189,10 @@ def mlp(x16: torch.Tensor, B: int, T: int, w1: torch.Tensor, b1: torch.Tensor, w
         raise KWSError(f"x rows {R} != B*T = {B * T}")
     if tuple(w1.shape) != (Cc, H, D) or tuple(w2.shape) != (Cc, P, H):
         raise KWSError("projector weight shapes do not match x")
+    if mask is not None and tuple(mask.shape) != (B, Cc, T):
+        # the epilogue indexes mask[(b*C + c)*T + t]: any other shape would be mis-indexed or read out of bounds
+        # (the reference raises a broadcast error, model.py:187-191)
+        raise KWSError(f"mask must be [B,C,T]=({B},{Cc},{T}), got {tuple(mask.shape)}")
     hidden = torch.empty((Cc, R, H), dtype=dt, device=x_bf16.device)
     out_dt = {MLP_OUT_NORM_F16: torch.float16, MLP_OUT_RAW_F32: torch.float32, MLP_OUT_RAW_16: dt}[out_mode]
     out = torch.empty((Cc, B, T, P), dtype=out_dt, device=x_bf16.device)
@@ -168,6 +203,7 @@ def mlp(x16: torch.Tensor, B: int, T: int, w1: torch.Tensor, b1: torch.Tensor, w
     return out
 
 
+@_guard
 def temporal(proj16: torch.Tensor, w16: torch.Tensor, bf: torch.Tensor, mask: Optional[torch.Tensor],
              eps: float = SIM_EPS) -> torch.Tensor:
     """proj fp16|bf16 [C,B,T,P] (mlp(..., MLP_OUT_RAW_16)) -> fp16 [C,B,ceil(T/2),P];
@@ -195,6 +231,7 @@ def pitch_for(Tu: int) -> int:
     return (Tu + 7) // 8 * 8
 
 
+@_guard
 def sim(kwd_n: torch.Tensor, utt_n: torch.Tensor, want_f32: bool, want_f16: bool, diag: bool = False,
         out_f32: Optional[torch.Tensor] = None, out_f16: Optional[torch.Tensor] = None):
     """kwd_n fp16 [C,K,Tk,Dk], utt_n fp16 [C,U,Tu,Dk] ->
@@ -220,6 +257,7 @@ def sim(kwd_n: torch.Tensor, utt_n: torch.Tensor, want_f32: bool, want_f16: bool
     return f32, f16
 
 
+@_guard
 def stem(feat_f16: torch.Tensor, Tu: int, w_packed: torch.Tensor, bias: torch.Tensor, out_mode: int,
          out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
     """feat_f16 fp16 [..., C, Tk, pitch] -> NCHW fp32 [N,64,Ho,Wo] or channels_last bf16 (logical
@@ -251,6 +289,7 @@ def sim_stem_supported(Cc: int, Tk: int, Tu: int, Dk: int, out_mode: int = STEM_
     return r == 1 or (r == 2 and out_mode == STEM_OUT_NHWC_BF16)
 
 
+@_guard
 def sim_stem(kwd_n: torch.Tensor, utt_n: torch.Tensor, w_fused: torch.Tensor, bias: torch.Tensor, out_mode: int,
              diag: bool = False, out: Optional[torch.Tensor] = None, k_range: Optional[Tuple[int, int]] = None,
              u_range: Optional[Tuple[int, int]] = None, per_keyword: bool = False) -> torch.Tensor:
@@ -293,6 +332,7 @@ def sim_stem(kwd_n: torch.Tensor, utt_n: torch.Tensor, w_fused: torch.Tensor, bi
     return view
 
 
+@_guard
 def interp_rows(x: torch.Tensor, layer_idx: Sequence[int], T_out: int, eps: float = SIM_EPS) -> torch.Tensor:
     """x fp32 [B,Cin,T,D] -> fp16 [C,B,T_out,D]: bilinear (align_corners=False) resampling of the L2-normalised
     frames along T (config #4: the width map of the image resize applied to the utterance operand)."""
@@ -305,6 +345,7 @@ def interp_rows(x: torch.Tensor, layer_idx: Sequence[int], T_out: int, eps: floa
     return out
 
 
+@_guard
 def sim_operand(kwd_n: torch.Tensor, utt_n: torch.Tensor) -> torch.Tensor:
     """kwd_n fp16 [C,K,Tk,Dk] (Tk % 16 == 0), utt_n fp16 [C,U,Tu,Dk] -> similarity as a K-major fp16 operand
     [C, K*U, Tu, Tk] (item = k*U + u)."""
@@ -319,6 +360,7 @@ def sim_operand(kwd_n: torch.Tensor, utt_n: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@_guard
 def resize_row_weights(src_h: Optional[torch.Tensor], K: int, Cc: int, Hp: int, Ho: int, device=None) -> torch.Tensor:
     """Height map of the bilinear resize as an operand: fp16 [C,K,Ho,Hp] (src_h int32 [K] valid frames, or None)."""
     lib = _lib.load()
@@ -331,6 +373,7 @@ def resize_row_weights(src_h: Optional[torch.Tensor], K: int, Cc: int, Hp: int, 
     return out
 
 
+@_guard
 def resize_bilinear(feat_f32: torch.Tensor, src_h: Optional[torch.Tensor], size: Tuple[int, int],
                     want_f32: bool = False, want_f16: bool = True):
     """feat fp32 [K,U,C,Hs,Ws] (+ src_h int32 [K]: valid rows per keyword) -> bilinear (align_corners=False)
@@ -349,6 +392,7 @@ def resize_bilinear(feat_f32: torch.Tensor, src_h: Optional[torch.Tensor], size:
     return o32, o16
 
 
+@_guard
 def maxpool_nhwc(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """MaxPool2d(3, 2, 1) of a channels-last bf16 activation (logical [N,C,H,W], physical [N,H,W,C]) ->
     channels-last bf16 [N,C,ceil(H/2),ceil(W/2)]; bit-identical to F.max_pool2d."""
@@ -370,6 +414,7 @@ def maxpool_nhwc(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.T
 
 
 # ---- scores ------------------------------------------------------------------------
+@_guard
 def scores(logits: torch.Tensor, hotword_mask: Optional[torch.Tensor], threshold: float):
     """logits fp32 [n,2] -> (scores fp32 [n], detections uint8 [n])"""
     lib = _lib.load()
@@ -384,6 +429,7 @@ def scores(logits: torch.Tensor, hotword_mask: Optional[torch.Tensor], threshold
     return sc, det
 
 
+@_guard
 def topk(scores_cu: torch.Tensor, k: int, ids: Optional[torch.Tensor] = None, id_offset: int = 0):
     """scores fp32 [n_cand,U] (+ ids int32 [n_cand,U]) -> (top scores [k,U], top ids int32 [k,U]);
     ties broken by the lower id."""
@@ -391,6 +437,13 @@ def topk(scores_cu: torch.Tensor, k: int, ids: Optional[torch.Tensor] = None, id
     n, U = scores_cu.shape
     os_ = torch.empty((k, U), dtype=torch.float32, device=scores_cu.device)
     oi = torch.empty((k, U), dtype=torch.int32, device=scores_cu.device)
+    ws_bytes = lib.kws_topk_workspace_bytes(n, U, int(k))
+    ws = torch.empty(ws_bytes // 8, dtype=torch.int64, device=scores_cu.device) if ws_bytes else None
+    levels, m = 1, n
+    while m > 2048:  # one launch per selection level (segments of 2048 candidates keep k survivors each)
+        m = (m + 2047) // 2048 * int(k)
+        levels += 1
     check(lib.kws_topk(_cuda(scores_cu, "scores", torch.float32), _cuda(ids, "ids", torch.int32), n, U,
-                       int(id_offset), int(k), _cuda(os_, "out_scores"), _cuda(oi, "out_ids"), _stream()), "kws_topk")
+                       int(id_offset), int(k), _cuda(os_, "out_scores"), _cuda(oi, "out_ids"), _cuda(ws, "workspace"),
+                       _stream()), "kws_topk", launches=levels)
     return os_, oi

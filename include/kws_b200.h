@@ -15,8 +15,13 @@
  *  - all data pointers are DEVICE pointers owned by the caller, 16-byte aligned;
  *    nothing is allocated, freed or synchronised inside the library;
  *  - `stream` is a cudaStream_t passed as void*; work is enqueued on it;
- *  - re-entrant from several host threads on different streams (the only global
- *    state is a one-time driver entry-point lookup and cached device attributes);
+ *  - re-entrant from several host threads on different streams: the only global
+ *    state is a one-time driver entry-point lookup (std::call_once) and cached
+ *    device attributes (atomics).  No environment variable is read and no setter
+ *    is exported; the development hooks (kws_debug_*, KWS_FUSED_* variables) exist
+ *    only in the separate -DKWS_DEBUG_HOOKS flavour libkws_b200_dbg.so;
+ *  - kernels are launched on the CURRENT device (cudaGetDevice): callers make the
+ *    device of their pointers current first (the Python front end does);
  *  - layouts are row-major with the last index contiguous.
  *
  * "Layer-major" operand layout: compressed keyword / utterance embeddings are
@@ -34,7 +39,7 @@
 extern "C" {
 #endif
 
-#define KWS_ABI_VERSION 6
+#define KWS_ABI_VERSION 7
 
 /* 16-bit operand formats (same encoding as the tcgen05 kind::f16 descriptor) */
 #define KWS_F16 0  /* IEEE half: 10-bit mantissa; for L2-normalised data and sane weights */
@@ -101,7 +106,9 @@ int kws_cast_f32_to_16(const float* src, void* dst16, size_t n, int dtype16, voi
  * (model.py:214-216), the layer slice x[-n_layers:] (dataset.py:570-573) and
  * the two mask multiplies (model.py:187-191).
  *   x fp32 [B,Cin,T,D]; layer_idx HOST int32 [C] (indices into Cin)
- *   mask fp32 [B,C,T] or NULL; out fp16 [C,B,T,D]                             */
+ *   mask fp32 [B,C,T] or NULL; out fp16 [C,B,T,D]
+ *   eps < 0: no normalisation (rows used as given: selection + mask + saturating-free fp16 cast) -- config #4,
+ *   whose caller normalises without eps beforehand (src/model/cb_whisper.py:106) and then does a plain matmul  */
 int kws_normalize_rows(const float* x, int B, int Cin, int T, int D, const int32_t* layer_idx, int C,
                        const float* mask, float eps, void* out_f16, void* stream);
 
@@ -192,7 +199,8 @@ int kws_resize_bilinear(const float* feat_f32, const int32_t* src_h, int K, int 
  * F.interpolate(bilinear, align_corners=False)).  The bilinear resize is linear and separable and the similarity
  * image is bilinear in its operands, so resize(kwd . utt^T) = (Wy kwd) . (Wx utt)^T:
  *   kws_interp_rows        applies Wx to the utterance frames: x fp32 [B,Cin,T,D] -> out fp16 [C,B,T_out,D], every
- *                          source frame L2-normalised first (like kws_normalize_rows), D % 8 == 0, D <= 1280
+ *                          source frame L2-normalised first (like kws_normalize_rows; eps < 0: frames used as
+ *                          given, like the reference's plain matmul), D % 8 == 0, D <= 1280
  *   kws_sim_operand        native-resolution similarity as a K-major fp16 operand: kwd_n [C,K,Tk,Dk] (Tk % 16 == 0,
  *                          zero-padded frames), utt_n [C,U,Tu,Dk] -> out fp16 [C, K*U, Tu, Tk], item = k*U + u
  *   kws_resize_row_weights Wy as an operand: out fp16 [C,K,Ho,Hp]; row i holds the two bilinear taps of output row i
@@ -223,12 +231,16 @@ int kws_scores(const float* logits, const float* hotword_mask, size_t n, float t
 /* Per-utterance top-k over the keyword axis with deterministic tie-break
  * (lower global keyword index first); used for the local top-k of a keyword
  * shard and for merging the all-gathered candidates (replaces torch.topk,
- * model.py:523).
+ * model.py:523).  Segmented bitonic selection on 64-bit (score, id) keys: every
+ * level reads its input once (coalesced over neighbouring utterances), any n_cand.
  *   scores fp32 [n_cand, U] (candidate-major), ids int32 [n_cand, U] or NULL
  *   (NULL: candidate c has global id id_offset + c)
- *   out_scores fp32 [k, U], out_ids int32 [k, U]; k <= 1024                     */
+ *   out_scores fp32 [k, U], out_ids int32 [k, U]; k <= 1024; rows beyond the number of
+ *   candidates hold (-inf, -1)
+ *   workspace: kws_topk_workspace_bytes(n_cand, U, k) bytes, 8-byte aligned (0 bytes / NULL for n_cand <= 2048) */
 int kws_topk(const float* scores, const int32_t* ids, int n_cand, int U, int id_offset, int k, float* out_scores,
-             int32_t* out_ids, void* stream);
+             int32_t* out_ids, void* workspace, void* stream);
+size_t kws_topk_workspace_bytes(int n_cand, int U, int k);
 
 #ifdef __cplusplus
 }

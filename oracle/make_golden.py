@@ -151,15 +151,99 @@ def load_case(name: str):
     return meta, ins, sd, outs
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# Config #4 (original CB-Whisper classifier): images from the UNMODIFIED CBWhisper._calculate_cosine_similarity_matrices_
+# (src/model/cb_whisper.py:189-210) and logits from the UNMODIFIED 12-channel classifier src/model/resnet.py:5-38 (what
+# src/model/model.py:78-93 runs on them).
+# ----------------------------------------------------------------------------------------------------------------
+CBW_CASE = dict(C=12, D=64, Tu=100, S=2, lens=(9, 21, 14, 64, 1), size=(30, 50), seed=41, body_seed=43)
+
+
+def cbw_inputs(case=CBW_CASE):
+    g = torch.Generator().manual_seed(case["seed"])
+    nrm = lambda t: t / torch.linalg.norm(t, dim=-1, keepdim=True)  # cb_whisper.py:106 (no eps)
+    kwd_list = [nrm(torch.randn(case["C"], t, case["D"], generator=g)) for t in case["lens"]]
+    utt = nrm(torch.randn(case["S"], case["C"], case["Tu"], case["D"], generator=g))
+    return kwd_list, utt
+
+
+def reference_cbw_resnet(body_seed: int):
+    """src/model/resnet.py (imports only torch + transformers), loaded where it lies; seeded init + non-trivial
+    stem BatchNorm statistics."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("ref_cbw_resnet", os.path.join(ref_stub.REFERENCE_SRC, "model", "resnet.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    torch.manual_seed(body_seed)
+    net = mod.Resnet(num_channels=12, num_classes=2).eval()
+    randomize_stem_bn(net, body_seed + 1)
+    return net
+
+
+def randomize_stem_bn(net, seed: int):
+    g = torch.Generator().manual_seed(seed)
+    bn = net.feature_extractor.embedder.embedder.normalization
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(64, generator=g) + 0.5), bn.bias.copy_(torch.randn(64, generator=g) * 0.1)
+        bn.running_mean.copy_(torch.randn(64, generator=g) * 0.1), bn.running_var.copy_(torch.rand(64, generator=g) + 0.5)
+
+
+def make_cbw_case(case=CBW_CASE):
+    kwd_list, utt = cbw_inputs(case)
+    imgs = ref_stub.reference_cbw_similarity(kwd_list, utt, case["size"])  # [K,S,C,h,w]
+    imgs_native = ref_stub.reference_cbw_similarity(kwd_list, utt, None)  # kws_features_size unset
+    net = reference_cbw_resnet(case["body_seed"])
+    grabbed = {}
+    h = net.feature_extractor.embedder.embedder.register_forward_hook(lambda m, i, o: grabbed.__setitem__("stem", o.detach().clone()))
+    with torch.inference_mode():
+        logits = net(imgs.flatten(0, 1)).view(len(kwd_list), case["S"], 2)
+    h.remove()
+    return {
+        "images": imgs.numpy(), "images_native_head": imgs_native[:, :, :2].numpy(),
+        "stem": grabbed["stem"].numpy().astype(np.float32), "logits": logits.numpy(),
+        "body_checksum": np.array(body_checksum(net), dtype=np.float64),
+    }
+
+
+def load_cbw_case(case=CBW_CASE):
+    """-> (kwd_list, utt, outputs dict, classifier with the attribute names of the reference wrapper, same_body)."""
+    z = np.load(os.path.join(GOLDEN_DIR, "cbw_small.npz"))
+    kwd_list, utt = cbw_inputs(case)
+    from transformers import ResNetConfig, ResNetModel
+
+    class _Net(torch.nn.Module):  # restated src/model/resnet.py:5-38 (same construction order => same seeded weights)
+        def __init__(self):
+            super().__init__()
+            self.config = ResNetConfig()
+            self.config.num_channels = 12
+            self.config.num_labels = 2
+            self.feature_extractor = ResNetModel(self.config)
+            self.classifier = torch.nn.Sequential(torch.nn.Flatten(1, -1), torch.nn.Linear(self.config.hidden_sizes[-1], 2, bias=True))
+
+    torch.manual_seed(case["body_seed"])
+    net = _Net().eval()
+    randomize_stem_bn(net, case["body_seed"] + 1)
+    ck = float(z["body_checksum"])
+    same = abs(body_checksum(net) - ck) <= 1e-9 * max(1.0, abs(ck))
+    return kwd_list, utt, {k: torch.from_numpy(z[k]) for k in z.files if k != "body_checksum"}, net, same
+
+
 def main():
     if not ref_stub.available():
         sys.exit("reference tree not present; golden fixtures can only be generated in the build container")
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    only = set(sys.argv[1:])
     for name in CASES:
+        if only and name not in only:
+            continue
         d = make_case(name)
         path = os.path.join(GOLDEN_DIR, f"kws_{name}.npz")
         np.savez_compressed(path, **d)
         print(f"{name}: wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
+    path = os.path.join(GOLDEN_DIR, "cbw_small.npz")
+    np.savez_compressed(path, **make_cbw_case())
+    print(f"cbw_small: wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
 
 
 if __name__ == "__main__":

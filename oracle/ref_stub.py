@@ -123,3 +123,44 @@ def build_reference_model(variant: str, C: int, D: int, P: int = 64, resnet_vers
     with contextlib.redirect_stdout(io.StringIO()):  # reference prints the threshold
         m = ref.KWSModel(**kw)
     return m.eval()
+
+
+def load_cbw_similarity_method():
+    """The UNMODIFIED ``CBWhisper._calculate_cosine_similarity_matrices_`` (src/model/cb_whisper.py:189-210) as a
+    plain function ``f(self, utt_hs, kwd_hs)``.
+
+    ``src/model/cb_whisper.py`` cannot be imported here (it needs ``whisper``, ``string2string``, ``pytorch_lightning``
+    and a sys.path hack at :10-11), so the method's source text is cut out of the file where it lies with ``ast`` and
+    exec'd with the three names it uses (``torch``, ``torchvision``, ``List``).  Nothing is copied into the repo.
+    ``self`` only needs ``self.hparams.kws_features_size``."""
+    import ast
+    from typing import List
+
+    import torch
+    import torchvision
+
+    path = os.path.join(REFERENCE_SRC, "model", "cb_whisper.py")
+    src = open(path).read()
+    tree = ast.parse(src)
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name == "_calculate_cosine_similarity_matrices_":
+            fn_src = ast.get_source_segment(src, node)
+            break
+    else:  # pragma: no cover
+        raise RuntimeError("_calculate_cosine_similarity_matrices_ not found in " + path)
+    import textwrap
+
+    ns = {"torch": torch, "torchvision": torchvision, "List": List}
+    exec(compile(textwrap.dedent(fn_src), path, "exec"), ns)
+    return ns["_calculate_cosine_similarity_matrices_"]
+
+
+def reference_cbw_similarity(kwd_list, utt_hs, size=(150, 750)):
+    """Run the unmodified method -> [K, S, C, size0, size1] (the reference returns a per-segment list of
+    [K, C, size0, size1]; stacked here keyword-major like the oracle)."""
+    import torch
+
+    fn = load_cbw_similarity_method()
+    self = types.SimpleNamespace(hparams=types.SimpleNamespace(kws_features_size=size))
+    per_seg = fn(self, utt_hs=utt_hs, kwd_hs=list(kwd_list))
+    return torch.stack(per_seg, dim=1)

@@ -68,7 +68,9 @@ def test_bad_arguments_are_rejected_without_a_device(built_lib):
     assert lib.kws_maxpool_nhwc(one, 1, 4, 4, 12, one, None) == -1
     assert b"multiple of 8" in lib.kws_last_error()
     # top-k limits
-    assert lib.kws_topk(one, None, 10, 1, 0, 2000, one, one, None) == -1
+    assert lib.kws_topk(one, None, 10, 1, 0, 2000, one, one, None, None) == -1
+    assert lib.kws_topk(one, None, 5000, 1, 0, 10, one, one, None, None) == -1  # more than one segment: workspace
+    assert lib.kws_topk_workspace_bytes(100, 4, 10) == 0 and lib.kws_topk_workspace_bytes(100000, 512, 200) > 0
     with pytest.raises(_lib.KWSError):
         _lib.check(-1, "kws_topk")
 

@@ -113,6 +113,51 @@ def test_score_detections_identical(built_lib, cuda_dev, name):
         assert float(sc.cpu()[ghosts].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("name", ["LE_small", "LEF_odd", "L_small"])
+def test_batched_steps_match_reference_outputs(built_lib, cuda_dev, name):
+    """test_step / validation_step override (all groups of a DataLoader item in one pass) on the GPU against what
+    the reference's steps produce from the golden logits: preds = softmax(logits)[:,1] * hotword_mask
+    (model.py:783-795), loss = sum over groups of the mean cross-entropy (model.py:348)."""
+    m, meta, x, outs, _ = build(name, cuda_dev, b200_return_features=False)
+    K, groups = meta["K"], [[0, 1], [2]]
+    labels = torch.tensor([1, 0, 1][:K], device=cuda_dev)
+    m.test_step_outputs, m.validation_step_outputs = [], []
+    for u in range(meta["U"]):
+        batch = {"utt": x["utt"][u], "utt_mask": x["um"][u], "kwd": [[x["kwd"][i] for i in g] for g in groups],
+                 "kwd_mask": [[x["km"][i] for i in g] for g in groups], "hotword_labels": [labels[g] for g in groups],
+                 "hotword_mask": [x["hot"][g] for g in groups], "speaker": f"s{u}"}
+        m.test_step(dict(batch), u)
+        m.validation_step(dict(batch), u, dataloader_idx=1)
+        t, v = m.test_step_outputs[-1], m.validation_step_outputs[1][-1]
+        assert t["speaker"] == f"s{u}" and torch.equal(t["targets"], labels) and torch.equal(v["targets"], labels)
+        assert err(t["preds"], outs["scores"][:, u]) <= TOL and torch.equal(t["preds"], v["preds"])
+        gl = outs["logits"][:, u]
+        exp_loss = sum(torch.nn.functional.cross_entropy(gl[g], labels.cpu()[g]) for g in groups)
+        assert abs(float(v["loss"]) - float(exp_loss)) <= 2 * TOL
+    assert len(m.validation_step_outputs) == 2
+
+
+def test_forward_reuses_the_compressed_utterance_across_groups(built_lib, cuda_dev):
+    """Callers that loop over keyword groups with the same utterance tensor (the reference test_step, model.py:769-780)
+    compress the utterance once; an in-place change of the tensor invalidates the cache."""
+    from enhance_cb_whisper_b200 import ops
+
+    m, meta, x, outs, _ = build("LE_small", cuda_dev)
+    utt, um = x["utt"][0], x["um"][0]
+    r0 = m(kwd_features=x["kwd"][:2], utt_features=utt.unsqueeze(0), kwd_mask=x["km"][:2], utt_mask=um.unsqueeze(0))
+    n0 = ops.LAUNCHES
+    r1 = m(kwd_features=x["kwd"][2:], utt_features=utt.unsqueeze(0), kwd_mask=x["km"][2:], utt_mask=um.unsqueeze(0))
+    n1 = ops.LAUNCHES
+    assert err(torch.cat([r0.logits, r1.logits]), outs["logits"][:, 0]) <= TOL
+    utt.mul_(1.0)  # bumps the version counter: same values, but the cache must not assume that
+    m(kwd_features=x["kwd"][2:], utt_features=utt.unsqueeze(0), kwd_mask=x["km"][2:], utt_mask=um.unsqueeze(0))
+    n2 = ops.LAUNCHES
+    assert n2 - n1 > n1 - n0  # the third call compressed the utterance again, the second did not
+    utt.zero_()
+    r3 = m(kwd_features=x["kwd"][2:], utt_features=utt.unsqueeze(0), kwd_mask=x["km"][2:], utt_mask=um.unsqueeze(0))
+    assert float(r3.features.abs().max()) == 0.0
+
+
 def test_training_style_batch_is_diagonal(built_lib, cuda_dev):
     """utt batch == keyword batch: pair k with utterance k (model.py:171-173; training_step batches)."""
     m, meta, x, outs, _ = build("LE_small", cuda_dev)

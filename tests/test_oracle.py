@@ -92,6 +92,41 @@ def test_reference_training_style_batch_is_diagonal():
     assert torch.allclose(r.features, diag, atol=1e-6)
 
 
+@pytest.mark.skipif(not ref_stub.available(), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("size", [(15, 75), (150, 750), None])
+def test_cbw_oracle_matches_live_reference_method(size):
+    """Config #4: the restated similarity + resize == the UNMODIFIED CBWhisper._calculate_cosine_similarity_matrices_
+    (src/model/cb_whisper.py:189-210, source exec'd where it lies; torchvision resize(antialias=False))."""
+    g = torch.Generator().manual_seed(1)
+    nrm = lambda t: t / torch.linalg.norm(t, dim=-1, keepdim=True)
+    kws = [nrm(torch.randn(12, t, 32, generator=g)) for t in (10, 37, 1, 64, 60)]
+    utt = nrm(torch.randn(2, 12, 300, 32, generator=g))
+    ref = ref_stub.reference_cbw_similarity(kws, utt, size)
+    got = O.cbw_similarity_resized(kws, utt, size=size)
+    assert ref.shape == got.shape
+    assert torch.equal(ref, got)
+    # not unit-norm inputs: the reference does a plain matmul on whatever it is given, so does the oracle
+    kws2 = [k * 3.0 for k in kws]
+    assert torch.equal(ref_stub.reference_cbw_similarity(kws2, utt, size), O.cbw_similarity_resized(kws2, utt, size=size))
+
+
+def test_cbw_oracle_matches_golden():
+    """The committed fixture (outputs of the unmodified reference method + src/model/resnet.py classifier)."""
+    from oracle.make_golden import CBW_CASE, load_cbw_case
+
+    kwd_list, utt, outs, net, same = load_cbw_case()
+    imgs = O.cbw_similarity_resized(kwd_list, utt, size=CBW_CASE["size"])
+    assert torch.equal(imgs, outs["images"])
+    native = O.cbw_similarity_resized(kwd_list, utt, size=None)
+    assert torch.equal(native[:, :, :2], outs["images_native_head"])
+    assert same, "regenerated classifier differs from the one the fixture was made with"
+    with torch.inference_mode():
+        st = O.stem(imgs.flatten(0, 1), {"model." + k: v for k, v in net.state_dict().items()})
+        assert torch.allclose(st, outs["stem"], atol=2e-5, rtol=1e-5)
+        logits = net.classifier(net.feature_extractor(imgs.flatten(0, 1)).pooler_output)
+    assert torch.allclose(logits.view(outs["logits"].shape), outs["logits"], atol=1e-4, rtol=1e-4)
+
+
 def test_cbw_similarity_resize_shapes():
     g = torch.Generator().manual_seed(1)
     kws = [torch.randn(12, t, 32, generator=g) for t in (10, 37)]

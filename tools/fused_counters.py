@@ -1,7 +1,10 @@
 """Development aid: per-CTA cycle breakdown of the fused kernel's MMA issuer (waits vs issue)."""
 import ctypes, os, sys
 import torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+# the hooks live in the development flavour only: KWS_FUSED_TIMERS=1 python enhance-cb-whisper_b200/build.py --debug-hooks
+os.environ.setdefault("KWS_B200_LIB", os.path.join(ROOT, "enhance-cb-whisper_b200", "libkws_b200_dbg.so"))
 from enhance_cb_whisper_b200 import ops, _lib
 
 dev = torch.device("cuda:0")
