@@ -44,6 +44,7 @@ SIGNATURES = {
     "kws_sim_stem": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "kws_sim_stem_supported": (_i, [_i, _i, _i, _i]),
     "kws_sim_stem_range": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "kws_sim_stem_ragged": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "kws_resize_bilinear": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "kws_interp_rows": (_i, [_vp, _i, _i, _i, _i, C.POINTER(C.c_int32), _i, _i, _f, _vp, _vp]),
     "kws_sim_operand": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),

@@ -69,13 +69,23 @@ class KeywordBank:
     kwd_n: torch.Tensor  # fp16 [C, K, Tk', Dk]: L2-normalised, frame mask folded
     lengths: torch.Tensor  # int32 [K] valid frames before compression (0 for ghosts)
     hotword_mask: torch.Tensor  # fp32 [K]: 0 for ghost keywords, 1 otherwise
+    lef: bool = False  # kwd_n is at pooled resolution ceil(T/2) (LEF variant)
 
     @property
     def K(self) -> int:
         return self.kwd_n.shape[1]
 
     def shard(self, lo: int, hi: int) -> "KeywordBank":
-        return KeywordBank(self.kwd_n[:, lo:hi].contiguous(), self.lengths[lo:hi], self.hotword_mask[lo:hi])
+        return KeywordBank(self.kwd_n[:, lo:hi].contiguous(), self.lengths[lo:hi], self.hotword_mask[lo:hi], self.lef)
+
+    def compressed_lengths(self) -> torch.Tensor:
+        """int32 [K]: valid frames at the resolution of ``kwd_n`` (LEF halves the frame axis: mask[..., ::2] keeps
+        ceil(len / 2) frames) -- the length table of kws_sim_stem_ragged."""
+        Tc = self.kwd_n.shape[2]
+        lens = self.lengths.to(torch.int32)
+        if self.lef:
+            lens = (lens + 1) // 2
+        return torch.clamp(lens, max=Tc).to(torch.int32).contiguous()
 
 
 @torch.no_grad()
@@ -139,7 +149,7 @@ def build_keyword_bank(model, items: Iterable[Optional[torch.Tensor]], n_frames:
     flush()
     kwd_n = outs[0] if len(outs) == 1 else torch.cat(outs, dim=1)
     return KeywordBank(kwd_n.contiguous(), torch.tensor(lens, dtype=torch.int32, device=device),
-                       torch.tensor(hot, dtype=torch.float32, device=device))
+                       torch.tensor(hot, dtype=torch.float32, device=device), lef)
 
 
 @torch.no_grad()
@@ -151,4 +161,5 @@ def score_bank(model, bank: KeywordBank, utt_features: torch.Tensor, utt_mask: t
     C = model.hparams.n_layers
     utt = utt_features[:, -C:].contiguous() if utt_features.shape[1] != C else utt_features
     utt_n = eng.compress(utt.to(bank.kwd_n.device), utt_mask.to(bank.kwd_n.device), list(range(C)))
-    return model.score_compressed(bank.kwd_n, utt_n, bank.hotword_mask, max_pairs, threshold)
+    return model.score_compressed(bank.kwd_n, utt_n, bank.hotword_mask, max_pairs, threshold,
+                                  kwd_len=bank.compressed_lengths())

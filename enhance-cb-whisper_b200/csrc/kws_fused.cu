@@ -122,6 +122,8 @@ struct FusedParams {
   int per_kw_u;  // KWS_PAIRS_PER_KEYWORD: utterance-side operand of pair (k, u) is bank item k * per_kw_u + u (else 0)
   int prefetch;  // multi-pass partial sums of step n+1: 1 = loaded into a second staging set during step n;
                  // 2 = pulled into L2 only (TMA prefetch), loaded and awaited in step n+1; 0 = neither
+  const int32_t* kwd_len;  // optional [K]: valid frames of every keyword (rows >= len are zero in kwd_n); output rows whose
+                           // receptive field lies beyond are relu(bias): no similarity, no stem MMAs, constant fill
   long long num_items;
   long long* dbg;  // optional [grid][16] cycle counters (issuer 0-4, epilogue 5-7, converter 8-11; development aid), or null
 };
@@ -201,12 +203,50 @@ __device__ __forceinline__ ItemCoord decode_item(const FusedParams& p, long long
   return r;
 }
 
+// Ragged keywords: the live part of an item.  Keyword frames >= L are zero rows of the operand bank (the 0/1 frame mask
+// is folded in as a row scale), so similarity rows >= L are exactly zero and an output row oi whose receptive field
+// [2oi-3, 2oi+3] starts at or beyond L is exactly relu(bias).  Live output rows: oi with max(0, 2oi-3) < L.
+struct ItemShape {
+  int L;   // valid keyword frames (<= Tk)
+  int nP;  // live stem steps (2 output rows each); steps [nP, p.nP) are constant fills
+  int nQ;  // quanta (4 input rows) the live steps read
+};
+template <bool RAGGED>
+__device__ __forceinline__ int item_len(const FusedParams& p, long long it) {
+  if constexpr (!RAGGED) return 0;  // unused
+  if (p.kwd_len == nullptr || it >= p.num_items) return p.Tk;
+  const int L = __ldg(p.kwd_len + decode_item(p, it).kw);
+  return L < 0 ? 0 : (L > p.Tk ? p.Tk : L);
+}
+template <bool RAGGED>
+__device__ __forceinline__ ItemShape item_shape(const FusedParams& p, int L) {
+  ItemShape r;
+  if constexpr (!RAGGED) {  // dense: launch constants, no registers
+    r.L = p.Tk, r.nP = p.nP, r.nQ = p.nQ;
+    return r;
+  }
+  r.L = L;
+  if (L >= p.Tk) {
+    r.nP = p.nP;
+  } else if (L <= 0) {
+    r.nP = 0;
+  } else {
+    int rows = (L + 2) / 2 + 1;
+    if (rows > p.Ho) rows = p.Ho;
+    r.nP = (rows + 1) >> 1;
+  }
+  r.nQ = r.nP > 0 ? r.nP + 2 : 0;
+  return r;
+}
+
 // NHWC: bf16 channels-last through TMA stores; else fp32 NCHW with direct stores (parity).  ROWS: see above.
 // MULTI: channel-group passes (acc_mode 1..3) compiled in; single-pass launches use the leaner instance.
 // NHM: output channels / 16 per TMEM round trip of the multi-pass epilogue (1 | 2).
 // S12: the shape parameters of the 12-layer, Dk = 64 case (LE / LEF models: cfg2, the full groups of cfg3 / cfg5) are
 // compile-time constants -- the issuer loops are sensitive to every instruction (a run-time stage count cost 10 %).
-template <bool NHWC, int ROWS, bool MULTI, int NHM = 2, bool S12 = false>
+// RAGGED: keyword length table honoured (p.kwd_len); the dense instances carry none of its bookkeeping -- the role loops
+// are sensitive to every live register and instruction.
+template <bool NHWC, int ROWS, bool MULTI, int NHM = 2, bool S12 = false, bool RAGGED = false>
 __global__ void __launch_bounds__(G_THREADS, 1)
 kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_constant__ CUtensorMap map_kwd,
                  const __grid_constant__ CUtensorMap map_out_lo, const __grid_constant__ CUtensorMap map_out_hi,
@@ -301,11 +341,15 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       [[maybe_unused]] uint32_t tr_stage = 0;
+      int L_next = item_len<RAGGED>(p, blockIdx.x);
       for (long long it = blockIdx.x; it < p.num_items; it += gridDim.x) {
         const ItemCoord w = decode_item(p, it);
+        const ItemShape sh = item_shape<RAGGED>(p, L_next);
+        L_next = item_len<RAGGED>(p, it + gridDim.x);
+        const int n_chunks = (sh.nQ + QPC - 1) / QPC;
         const int jbase = 2 * G_TILE_OJ * w.ct - 3;  // input column of pixel x = 0 (OOB columns read as zero)
-        for (int n = 0; n < p.n_chunks; ++n) {
-          if (ROWS * n - 3 >= p.Tk) continue;  // chunk entirely below the image (conv zero padding): nothing to load
+        for (int n = 0; n < n_chunks; ++n) {
+          if (ROWS * n - 3 >= sh.L) continue;  // chunk entirely below the image / the keyword (zero rows): nothing to load
           for (int c = 0; c < kC; ++c) {
             for (int kb = 0; kb < kNkb; ++kb) {
               mbar_wait(&oempty[stage], phase ^ 1, 100 + stage);
@@ -333,9 +377,13 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
       int o_stage = 0;
       uint32_t o_phase = 0, g = 0;
       [[maybe_unused]] uint32_t tr_s = 0;
+      int L_next = item_len<RAGGED>(p, blockIdx.x);
       for (long long it = blockIdx.x; it < p.num_items; it += gridDim.x) {
-        for (int n = 0; n < p.n_chunks; ++n, ++g) {
-          if (ROWS * n - 3 >= p.Tk) {
+        const ItemShape sh = item_shape<RAGGED>(p, L_next);
+        L_next = item_len<RAGGED>(p, it + gridDim.x);
+        const int n_chunks = (sh.nQ + QPC - 1) / QPC;
+        for (int n = 0; n < n_chunks; ++n, ++g) {
+          if (ROWS * n - 3 >= sh.L) {
             // all-zero chunk: no operands, no MMAs; keep the tile hand-shake (the converters write zeros without
             // reading the tiles)
             for (int j = 0; 2 * j < kC; ++j) {
@@ -386,9 +434,12 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
       uint32_t acc_seq = 0;  // global stem step counter -> accumulator buffer
       long long tm_acc = 0, tm_q = 0, tm_issue = 0;
       const long long tm_start = KWS_CLK();
+      int L_next = item_len<RAGGED>(p, blockIdx.x);
       for (long long it = blockIdx.x; it < p.num_items; it += gridDim.x) {
+        const ItemShape sh = item_shape<RAGGED>(p, L_next);
+        L_next = item_len<RAGGED>(p, it + gridDim.x);
         int waited = 0;  // quanta of this item known to be in the ring
-        for (int P = 0; P < p.nP; ++P, ++acc_seq) {
+        for (int P = 0; P < sh.nP; ++P, ++acc_seq) {
           const uint32_t acc = acc_seq & 1;
           const long long t1 = KWS_CLK();
           KWS_TRACE(0, acc_seq, 0);
@@ -396,7 +447,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
           KWS_TRACE(0, acc_seq, 1);
           const long long t2 = KWS_CLK();
           // kernel rows 0..5 read quanta P and P+1 only; quantum P+2 (input row 4P+5) is first touched by di = 6
-          while (waited <= P + 1 && waited < p.nQ) {  // first step of an item only
+          while (waited <= P + 1 && waited < sh.nQ) {  // first step of an item only
             const uint32_t G = qbase + waited;
             mbar_wait(&qfull[G & 3], (G >> 2) & 1, 400 + (int)(G & 3));
             ++waited;
@@ -412,7 +463,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
             if (di == 6) {
               const long long u0 = KWS_CLK();
               KWS_TRACE(0, acc_seq, 3);
-              while (waited <= P + 2 && waited < p.nQ) {
+              while (waited <= P + 2 && waited < sh.nQ) {
                 const uint32_t G = qbase + waited;
                 mbar_wait(&qfull[G & 3], (G >> 2) & 1, 400 + (int)(G & 3));
                 ++waited;
@@ -443,8 +494,8 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
           tm_issue += KWS_CLK() - t3;
         }
         // the two tail quanta were read by the last step only
-        for (int q = p.nP; q < p.nQ; ++q) umma_commit(&qempty[(qbase + q) & 3]);
-        qbase += p.nQ;
+        for (int q = sh.nP; q < sh.nQ; ++q) umma_commit(&qempty[(qbase + q) & 3]);
+        qbase += sh.nQ;
       }
       if (p.dbg) {
         long long* o = p.dbg + (size_t)blockIdx.x * 32;
@@ -504,11 +555,16 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
     }
     long long te_wait = 0, te_ld = 0, te_rest = 0, te_pl = 0, te_lds = 0;
     long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int L_next = item_len<RAGGED>(p, blockIdx.x);
+    bool stage_const = false;  // this warp's staging tile holds the constant relu(bias) tile of the fill steps
     for (long long it = blockIdx.x; it < p.num_items; it += gridDim.x) {
       const ItemCoord w = decode_item(p, it);
+      const ItemShape sh = item_shape<RAGGED>(p, L_next);
+      L_next = item_len<RAGGED>(p, it + gridDim.x);
       const int oj = w.ct * G_TILE_OJ + ojl;
       const bool col_ok = ojl < G_TILE_OJ && oj < p.Wo;
-      for (int P = 0; P < p.nP; ++P, ++acc_seq) {
+      for (int P = 0; P < sh.nP; ++P, ++acc_seq) {
+        stage_const = false;
         const uint32_t acc = acc_seq & 1;
         const long long e0 = KWS_CLK();
         mbar_wait(&afull[acc], (acc_seq >> 1) & 1, 600 + acc);
@@ -549,8 +605,8 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
                 if (tile_ok) load_prev(0u, w.ct, oi, (int)w.pair);  // awaited below, in this step
                 if (p.prefetch == 2) {  // next step's tile: HBM -> L2 now, so that its load is an L2 hit
                   int nct = w.ct, noi = oi + 2, npair = (int)w.pair;
-                  bool have = P + 1 < p.nP;
-                  if (!have && it + gridDim.x < p.num_items) {
+                  bool have = P + 1 < sh.nP;
+                  if (!have && it + gridDim.x < p.num_items && item_shape<RAGGED>(p, L_next).nP > 0) {
                     const ItemCoord wn = decode_item(p, it + gridDim.x);
                     nct = wn.ct, noi = row_sel, npair = (int)wn.pair, have = true;
                   }
@@ -562,7 +618,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
                 }
               } else if (nhwc && MULTI && loads_prev) {
                 // the other staging set is free now (its store has been read): prefetch the next step's partial sums
-                if (P + 1 < p.nP) {
+                if (P + 1 < sh.nP) {
                   if (tile_ok_at(w.ct, oi + 2)) load_prev(set ^ 1u, w.ct, oi + 2, (int)w.pair);
                 } else if (it + gridDim.x < p.num_items) {
                   const ItemCoord wn = decode_item(p, it + gridDim.x);
@@ -697,6 +753,65 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
         if (warp == 4 && lane == 0) KWS_TRACE(1, acc_seq, 2);
         tp[6] += KWS_CLK() - tp[7];
       }
+      // ---- fill steps (ragged keywords): output rows beyond the keyword are exactly relu(bias) --------------------
+      // Only the pass that writes final values fills (single pass / last channel-group pass); the partial sums of the
+      // earlier passes are never read for these rows.
+      if (RAGGED && sh.nP < p.nP && (!MULTI || p.acc_mode == 0 || p.acc_mode == 3)) {
+        const uint32_t t_bias = tmem_base + G_TMEM_BIAS + ((uint32_t)(q * 32) << 16);
+        if constexpr (nhwc) {
+          if (!stage_const) {
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // staging tile free again
+            __syncwarp();
+            uint8_t* srow = stage0 + lane * 128;
+#pragma unroll 1
+            for (int ch = 0; ch < 4; ++ch) {
+              uint32_t vbias[16];
+              tmem_ld16(t_bias + ch * 16, vbias);
+              tmem_ld_wait();
+              uint32_t o[8];
+#pragma unroll
+              for (int e = 0; e < 16; e += 2) o[e >> 1] = relu_bf16x2(pack_b64(vbias[e], vbias[e + 1]));
+              if (lo_warp || lane < G_TILE_OJ - 32) {
+                *reinterpret_cast<uint4*>(srow + (((2 * ch) ^ (lane & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<uint4*>(srow + (((2 * ch + 1) ^ (lane & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+              }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            stage_const = true;
+          }
+          if (lane == 0) {
+            for (int P = sh.nP; P < p.nP; ++P) {
+              const int oi = 2 * P + row_sel;
+              if (!tile_ok_at(w.ct, oi)) continue;
+              asm volatile(
+                  "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                      reinterpret_cast<uint64_t>(my_map)),
+                  "r"(smem_u32(stage0)), "r"(0), "r"(w.ct * G_TILE_OJ + (q & 1) * 32), "r"(oi), "r"((int)w.pair)
+                  : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          __syncwarp();
+        } else {
+          const long long oc_stride = (long long)p.Ho * p.Wo;
+#pragma unroll 1
+          for (int ch = 0; ch < 4; ++ch) {
+            uint32_t vbias[16];
+            tmem_ld16(t_bias + ch * 16, vbias);
+            tmem_ld_wait();
+            if (col_ok) {
+              for (int P = sh.nP; P < p.nP; ++P) {
+                const int oi = 2 * P + row_sel;
+                if (oi >= p.Ho) continue;
+                float* o32 = reinterpret_cast<float*>(p.out) + ((w.pair * G_OC) * p.Ho + oi) * (long long)p.Wo + oj;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) o32[(ch * 16 + e) * oc_stride] = fmaxf(__uint_as_float(vbias[e]), 0.f);
+              }
+            }
+          }
+        }
+      }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all stores complete before exit
     if (p.dbg && warp == 4 && lane == 0) {
@@ -718,9 +833,12 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
     uint32_t g = 0;   // global similarity chunk counter
     uint32_t Gq = 0;  // global quantum counter
     long long tc_sfull = 0, tc_qempty = 0, tc_ld = 0, tc_st = 0;
+    int L_next = item_len<RAGGED>(p, blockIdx.x);
     for (long long it = blockIdx.x; it < p.num_items; it += gridDim.x) {
-      for (int q0 = 0; q0 < p.nQ; q0 += QPC, ++g) {
-        const int nq = p.nQ - q0 < QPC ? p.nQ - q0 : QPC;
+      const ItemShape sh = item_shape<RAGGED>(p, L_next);
+      L_next = item_len<RAGGED>(p, it + gridDim.x);
+      for (int q0 = 0; q0 < sh.nQ; q0 += QPC, ++g) {
+        const int nq = sh.nQ - q0 < QPC ? sh.nQ - q0 : QPC;
         const long long c0 = KWS_CLK();
         const long long c1 = c0;
         if (warp == 8 && lane == 0) KWS_TRACE(2, g, 0);
@@ -729,7 +847,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
         uint32_t h2[ROWS][NPAIR];  // [row][layer pair] fp16x2
 #pragma unroll
         for (int j = 0; j < NPAIR; ++j) {
-          if (2 * j < kC && 4 * q0 - 3 >= p.Tk) {  // chunk entirely below the image: zeros, tiles untouched
+          if (2 * j < kC && 4 * q0 - 3 >= sh.L) {  // chunk entirely below the image / keyword: zeros, tiles untouched
             mbar_wait(&sfull[j], g & 1, 700 + j);
             mbar_arrive(&sempty[j]);
 #pragma unroll
@@ -990,7 +1108,17 @@ extern "C" int kws_sim_stem(const void* kwd_n, const void* utt_n, int C, int K, 
 extern "C" int kws_sim_stem_range(const void* kwd_n, const void* utt_n, int C, int K, int U, int Tk, int Tu, int Dk,
                                   int pair_mode, int k0, int nk, int u0, int nu, const void* w_fused,
                                   const float* bias, int out_mode, void* out, void* stream) {
+  return kws_sim_stem_ragged(kwd_n, utt_n, nullptr, C, K, U, Tk, Tu, Dk, pair_mode, k0, nk, u0, nu, w_fused, bias,
+                             out_mode, out, stream);
+}
+
+extern "C" int kws_sim_stem_ragged(const void* kwd_n, const void* utt_n, const int32_t* kwd_len, int C, int K, int U,
+                                   int Tk, int Tu, int Dk, int pair_mode, int k0, int nk, int u0, int nu,
+                                   const void* w_fused, const float* bias, int out_mode, void* out, void* stream) {
   KWS_CHECK_ARG(kwd_n && utt_n && w_fused && bias && out, "sim_stem: null pointer");
+  KWS_CHECK_ARG(kwd_len == nullptr || pair_mode != KWS_PAIRS_PER_KEYWORD,
+                "sim_stem: a keyword length table cannot be combined with KWS_PAIRS_PER_KEYWORD");
+  KWS_CHECK_ARG(kwd_len == nullptr || g_multi_prefetch != 1, "sim_stem: ragged keywords need prefetch mode 0 or 2");
   KWS_CHECK_ARG(C > 0 && K > 0 && U > 0 && Tk > 0 && Tu > 0, "sim_stem: non-positive dimension");
   KWS_CHECK_ARG(k0 >= 0 && nk > 0 && k0 + nk <= K, "sim_stem: keyword range [%d,%d) outside [0,%d)", k0, k0 + nk, K);
   KWS_CHECK_ARG(u0 >= 0 && nu > 0 && u0 + nu <= U, "sim_stem: utterance range [%d,%d) outside [0,%d)", u0, u0 + nu, U);
@@ -1063,6 +1191,7 @@ extern "C" int kws_sim_stem_range(const void* kwd_n, const void* utt_n, int C, i
   if (grid > sms) grid = sms;
   if (g_fused_grid_limit > 0 && grid > g_fused_grid_limit) grid = g_fused_grid_limit;
   p.dbg = g_fused_dbg;
+  p.kwd_len = kwd_len;
   const int n_groups = fused_groups(C);
   const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(w_fused);
   for (int g = 0; g < n_groups; ++g) {
@@ -1087,19 +1216,30 @@ extern "C" int kws_sim_stem_range(const void* kwd_n, const void* utt_n, int C, i
     }
     const bool nh = out_mode == KWS_STEM_OUT_NHWC_BF16;
     void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, FusedParams);
+    const bool s12 = Cg == 12 && p.nkb == 1 && g_fused_s12;
+    const bool ragged = kwd_len != nullptr;
+    KWS_CHECK_ARG(!ragged || nh || p.acc_mode == 0, "sim_stem: internal: multi-pass needs bf16 output");
     if (p.acc_mode != 0) {
-      kern = kws_fused_kernel<true, 16, true, 2>;
-#ifdef KWS_DEBUG_HOOKS
-      if (g_multi_nh == 1) kern = kws_fused_kernel<true, 16, true, 1>;
-#endif
-      if (g_multi_nh != 1 && Cg == 12 && p.nkb == 1 && g_fused_s12) kern = kws_fused_kernel<true, 16, true, 2, true>;
-      p.prefetch = g_multi_prefetch;
       KWS_CHECK_ARG(rows == 16 && nh, "sim_stem: internal: multi-pass needs 16-row chunks, bf16 output");
+      p.prefetch = g_multi_prefetch;
+      if (ragged)
+        kern = s12 ? kws_fused_kernel<true, 16, true, 2, true, true> : kws_fused_kernel<true, 16, true, 2, false, true>;
+      else
+        kern = s12 ? kws_fused_kernel<true, 16, true, 2, true> : kws_fused_kernel<true, 16, true, 2>;
+#ifdef KWS_DEBUG_HOOKS
+      if (g_multi_nh == 1 && !ragged) kern = kws_fused_kernel<true, 16, true, 1>;
+      KWS_CHECK_ARG(!(g_multi_nh == 1 && ragged), "sim_stem: ragged keywords need the 2-trip multi-pass epilogue");
+#endif
+    } else if (ragged) {  // the fp32 NCHW (parity) output has ragged instances too: score() with the fp32 body
+      kern = rows == 48 ? (nh ? kws_fused_kernel<true, 48, false, 2, false, true> : kws_fused_kernel<false, 48, false, 2, false, true>)
+             : rows == 32 ? (nh ? kws_fused_kernel<true, 32, false, 2, false, true> : kws_fused_kernel<false, 32, false, 2, false, true>)
+                          : (nh ? kws_fused_kernel<true, 16, false, 2, false, true> : kws_fused_kernel<false, 16, false, 2, false, true>);
+      if (rows == 16 && nh && s12) kern = kws_fused_kernel<true, 16, false, 2, true, true>;
     } else {
       kern = rows == 48 ? (nh ? kws_fused_kernel<true, 48, false> : kws_fused_kernel<false, 48, false>)
              : rows == 32 ? (nh ? kws_fused_kernel<true, 32, false> : kws_fused_kernel<false, 32, false>)
                           : (nh ? kws_fused_kernel<true, 16, false> : kws_fused_kernel<false, 16, false>);
-      if (rows == 16 && nh && Cg == 12 && p.nkb == 1 && g_fused_s12) kern = kws_fused_kernel<true, 16, false, 2, true>;
+      if (rows == 16 && nh && s12) kern = kws_fused_kernel<true, 16, false, 2, true>;
     }
     const size_t smem = g_smem_bytes(rows, p.n_mma, p.acc_mode != 0 && p.prefetch == 1);
     KWS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -133,6 +133,16 @@ class KWSEngine:
             out[:, b0:b1] = o
         return out
 
+    @staticmethod
+    def keyword_lengths(mask: torch.Tensor) -> torch.Tensor:
+        """mask [K,C,T'] (0/1 per frame, any layer) -> int32 [K]: 1 + index of the last frame that is unmasked in any
+        layer (0 if none).  Frames at or beyond it are zero rows of the compressed bank whatever the variant, because
+        the mask is folded in as a row scale."""
+        live = (mask != 0).any(dim=1)  # [K,T']
+        T = live.shape[1]
+        idx = torch.arange(1, T + 1, device=mask.device, dtype=torch.int32)
+        return (live.to(torch.int32) * idx).amax(dim=1).to(torch.int32).contiguous()
+
     # -- stage 2+3 over pair chunks -----------------------------------------------------
     def pair_chunks(self, K: int, U: int, Tk: int, Tu: int, max_pairs: int) -> Iterator[Tuple[int, int, int, int]]:
         """Tile the K x U pair grid into (k0,k1,u0,u1) blocks of at most max_pairs pairs.  Blocks are
@@ -152,13 +162,15 @@ class KWSEngine:
 
     def hot_path(self, kwd_n: torch.Tensor, utt_n: torch.Tensor, out_mode: int, max_pairs: int = 1024,
                  consume: Optional[Callable] = None, bufs: Optional[dict] = None,
-                 launch_events: Optional[list] = None):
+                 launch_events: Optional[list] = None, kwd_len: Optional[torch.Tensor] = None):
         """Similarity + stem for all pairs, chunked.  ``consume(k0,k1,u0,u1,stem_out)`` receives the
         stem activation of each chunk ([pairs,64,Ho,Wo], pair = (k-k0)*(u1-u0) + (u-u0));
         intermediate buffers are reused across chunks (``bufs``).  The fused kernel is used whenever it
         supports the shape (the similarity tensor then never exists in HBM); otherwise kws_sim + kws_stem.
         ``launch_events``: if a list, a (start, end) CUDA-event pair around every pair-kernel launch is
-        appended (bench.py reads per-launch durations from them)."""
+        appended (bench.py reads per-launch durations from them).  ``kwd_len``: int32 [K] valid frames of every
+        keyword at the similarity's resolution (``keyword_lengths``): the fused kernel then skips the rows beyond a
+        keyword (bit-identical output); ignored by the un-fused path."""
         Cc, K, Tk, Dk = kwd_n.shape
         _, U, Tu, _ = utt_n.shape
         bufs = bufs if bufs is not None else {}
@@ -178,7 +190,7 @@ class KWSEngine:
                 ev[0].record()
             if fused:
                 st = ops.sim_stem(kwd_n, utt_n, self.w.stem_wf, self.w.stem_b, out_mode, out=bufs[keyo],
-                                  k_range=(k0, k1), u_range=(u0, u1))
+                                  k_range=(k0, k1), u_range=(u0, u1), kwd_len=kwd_len)
             else:
                 kk = kwd_n[:, k0:k1].contiguous() if (k0, k1) != (0, K) else kwd_n
                 uu = utt_n[:, u0:u1].contiguous() if (u0, u1) != (0, U) else utt_n

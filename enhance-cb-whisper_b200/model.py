@@ -109,6 +109,8 @@ class B200ForwardMixin:
     b200_return_features: bool = True  # materialise KWSOutput.features (fp32) like the reference
     b200_layer_idx: Optional[Sequence[int]] = None  # explicit layer selection into the given stack
     b200_mlp_dtype: str = "float16"  # projector GEMM operands: "float16" (parity) | "bfloat16" (range-safe)
+    b200_ragged: bool = True  # batched scoring: carry the keyword lengths (from the frame masks) into the fused kernel,
+    #                           which skips the rows beyond a keyword -- bit-identical output (kws_sim_stem_ragged)
 
     def _b200_init(self):
         self._packed: Optional[PackedWeights] = None
@@ -207,7 +209,8 @@ class B200ForwardMixin:
             if not self.b200_return_features and eng.fused(Tk_s, Tu_s, out_mode):
                 # KWSOutput.features is read by no caller of the reference; without it the
                 # similarity tensor never reaches HBM
-                st = ops.sim_stem(kwd_n, utt_n, eng.w.stem_wf, eng.w.stem_b, out_mode, diag=diag)
+                st = ops.sim_stem(kwd_n, utt_n, eng.w.stem_wf, eng.w.stem_b, out_mode, diag=diag,
+                                  kwd_len=self._b200_kwd_len(kwd_mask))
             else:
                 f32, f16 = ops.sim(kwd_n, utt_n, want_f32=self.b200_return_features, want_f16=True, diag=diag)
                 st = ops.stem(f16, Tu_s, eng.w.stem_w, eng.w.stem_b, out_mode)
@@ -221,6 +224,12 @@ class B200ForwardMixin:
 
     def resnet_forward(self, input_features: torch.Tensor):
         return self.model(input_features)
+
+    def _b200_kwd_len(self, kwd_mask: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+        """int32 [K] keyword lengths at the similarity's resolution, from the 0/1 frame masks (None: dense)."""
+        if not self.b200_ragged or kwd_mask is None:
+            return None
+        return KWSEngine.keyword_lengths(kwd_mask)
 
     def _b200_compress_utt(self, eng: KWSEngine, utt: torch.Tensor, mask: torch.Tensor, layer_idx) -> torch.Tensor:
         """Utterance compression with a one-entry cache: callers that loop over keyword groups with the same
@@ -260,7 +269,7 @@ class B200ForwardMixin:
             logits[k0:k1, u0:u1] = self._body(st).float().view(k1 - k0, u1 - u0, 2)
 
         eng.hot_path(kwd_n, utt_n, ops.STEM_OUT_NHWC_BF16 if lowp else ops.STEM_OUT_NCHW_F32,
-                     int(getattr(self, "b200_step_pairs", 256)), consume)
+                     int(getattr(self, "b200_step_pairs", 256)), consume, kwd_len=self._b200_kwd_len(kwd_mask))
         return logits[:, 0]
 
     def _b200_step(self, batch, with_loss: bool):
@@ -315,71 +324,108 @@ class B200ForwardMixin:
         layer_idx = list(self.b200_layer_idx) if self.b200_layer_idx is not None else list(range(self.hparams.n_layers))
         kwd_n = eng.compress(kwd_features, kwd_mask, layer_idx)
         utt_n = eng.compress(utt_features, utt_mask, layer_idx)
-        return self.score_compressed(kwd_n, utt_n, hotword_mask, max_pairs, threshold)
+        return self.score_compressed(kwd_n, utt_n, hotword_mask, max_pairs, threshold,
+                                     kwd_len=self._b200_kwd_len(kwd_mask))
 
-    @torch.no_grad()
-    def score_host(self, kwd_features, utt_features, kwd_mask, utt_mask, hotword_mask=None, max_pairs: int = 256,
-                   threshold: Optional[float] = None, kwd_slab: int = 125, device=None):
-        """``score`` for inputs that live in (pinned) HOST memory -- what the reference's DataLoader hands to
-        ``test_step`` (model.py:749-765).  The keyword bank is uploaded slab by slab on a copy stream into two
-        staging buffers while the previous slab is compressed and scored on the current stream, so the PCIe
-        transfer of the raw fp32 embeddings (the largest tensor of the job: K x C x Tk x D x 4 bytes) hides
-        behind the compute.  Returns device tensors like ``score``."""
-        dev = torch.device(device) if device is not None else next(self.parameters()).device
-        if dev.type == "cuda" and dev.index is None:  # indexed, so that the cached copy stream / staging compare equal
-            dev = torch.device("cuda", torch.cuda.current_device())
-        if kwd_features.shape[0] == 0 or utt_features.shape[0] == 0:
-            return _empty_scores(kwd_features.shape[0], utt_features.shape[0], dev)
-        eng = self.prepare(dev)
-        layer_idx = list(self.b200_layer_idx) if self.b200_layer_idx is not None else list(range(self.hparams.n_layers))
-        K, U = kwd_features.shape[0], utt_features.shape[0]
+    def _host_slabs(self, name: str, x: torch.Tensor, mask: torch.Tensor, slab: int, dev: torch.device):
+        """Generator over device views (x_slab, mask_slab, i0, i1) of a HOST (ideally pinned) batch: slab i+1 is
+        uploaded on a copy stream into the other of two staging buffers while the caller works on slab i on the
+        current stream.  The caller must have finished *enqueueing* its use of a slab before asking for the next."""
+        n = x.shape[0]
+        slab = max(1, min(int(slab), n))
         cur = torch.cuda.current_stream(dev)
         if getattr(self, "_copy_stream", None) is None or self._copy_stream.device != dev:
             self._copy_stream = torch.cuda.Stream(dev)
             self._stage = {}
         cs = self._copy_stream
-        slab = max(1, min(int(kwd_slab), K))
-        key = (slab,) + tuple(kwd_features.shape[1:]) + tuple(kwd_mask.shape[1:])
-        if self._stage.get("key") != key:
-            self._stage = {"key": key,
-                           "kwd": [torch.empty((slab,) + tuple(kwd_features.shape[1:]), dtype=torch.float32, device=dev)
-                                   for _ in range(2)],
-                           "mask": [torch.empty((slab,) + tuple(kwd_mask.shape[1:]), dtype=torch.float32, device=dev)
-                                    for _ in range(2)],
-                           "free": [torch.cuda.Event() for _ in range(2)], "ready": [torch.cuda.Event() for _ in range(2)]}
-        stg = self._stage
-        utt_n = eng.compress(utt_features.to(dev, non_blocking=True), utt_mask.to(dev, non_blocking=True), layer_idx)
-        hot = hotword_mask.to(dev, non_blocking=True) if hotword_mask is not None else None
-        logits = torch.empty((K, U, 2), dtype=torch.float32, device=dev)
-        lowp = self.b200_body_dtype != "float32"
-        out_mode = ops.STEM_OUT_NHWC_BF16 if lowp else ops.STEM_OUT_NCHW_F32
+        key = (slab,) + tuple(x.shape[1:]) + tuple(mask.shape[1:])
+        stg = self._stage.get(name)
+        if stg is None or stg["key"] != key:
+            stg = self._stage[name] = {
+                "key": key,
+                "x": [torch.empty((slab,) + tuple(x.shape[1:]), dtype=torch.float32, device=dev) for _ in range(2)],
+                "mask": [torch.empty((slab,) + tuple(mask.shape[1:]), dtype=torch.float32, device=dev) for _ in range(2)],
+                "free": [torch.cuda.Event() for _ in range(2)], "ready": [torch.cuda.Event() for _ in range(2)]}
         for b in range(2):
             stg["free"][b].record(cur)
-        n_slabs = (K + slab - 1) // slab
+        n_slabs = (n + slab - 1) // slab
 
         def upload(i):
-            b, k0 = i & 1, i * slab
-            k1 = min(K, k0 + slab)
+            b, i0 = i & 1, i * slab
+            i1 = min(n, i0 + slab)
             cs.wait_event(stg["free"][b])
             with torch.cuda.stream(cs):
-                stg["kwd"][b][: k1 - k0].copy_(kwd_features[k0:k1], non_blocking=True)
-                stg["mask"][b][: k1 - k0].copy_(kwd_mask[k0:k1], non_blocking=True)
+                stg["x"][b][: i1 - i0].copy_(x[i0:i1], non_blocking=True)
+                stg["mask"][b][: i1 - i0].copy_(mask[i0:i1], non_blocking=True)
                 stg["ready"][b].record(cs)
 
         upload(0)
         for i in range(n_slabs):
-            b, k0 = i & 1, i * slab
-            k1 = min(K, k0 + slab)
+            b, i0 = i & 1, i * slab
+            i1 = min(n, i0 + slab)
             if i + 1 < n_slabs:
                 upload(i + 1)
             cur.wait_event(stg["ready"][b])
-            kwd_n = eng.compress(stg["kwd"][b][: k1 - k0], stg["mask"][b][: k1 - k0], layer_idx)
-            stg["free"][b].record(cur)
+            yield stg["x"][b][: i1 - i0], stg["mask"][b][: i1 - i0], i0, i1
+            stg["free"][b].record(cur)  # everything the caller enqueued on the current stream has read the slab
 
-            def consume(a0, a1, u0, u1, st, k0=k0):
-                logits[k0 + a0:k0 + a1, u0:u1] = self._body(st).float().view(a1 - a0, u1 - u0, 2)
+    @torch.no_grad()
+    def compress_host(self, features, mask, slab: int = 125, device=None, name: str = "kwd") -> torch.Tensor:
+        """HOST embeddings [B,Cin,T,D] (+ mask [B,C,T']) -> resident compressed operands fp16 [C,B,T',Dk]; the raw
+        fp32 tensor (the largest object of a job: B x C x T x D x 4 bytes) only ever exists on the device one slab
+        at a time, its upload overlapped with the compression of the previous slab."""
+        dev = self._b200_device(device)
+        eng = self.prepare(dev)
+        layer_idx = list(self.b200_layer_idx) if self.b200_layer_idx is not None else list(range(self.hparams.n_layers))
+        out = None
+        for xs, ms, i0, i1 in self._host_slabs(name, features, mask, slab, dev):
+            o = eng.compress(xs, ms, layer_idx)
+            if out is None:
+                if i1 - i0 == features.shape[0]:
+                    return o
+                out = torch.empty((o.shape[0], features.shape[0]) + tuple(o.shape[2:]), dtype=o.dtype, device=dev)
+            out[:, i0:i1] = o
+        return out
 
-            eng.hot_path(kwd_n, utt_n, out_mode, max_pairs, consume, bufs=stg.setdefault("bufs", {}))
+    def _b200_device(self, device=None) -> torch.device:
+        dev = torch.device(device) if device is not None else next(self.parameters()).device
+        if dev.type == "cuda" and dev.index is None:  # indexed, so that the cached copy stream / staging compare equal
+            dev = torch.device("cuda", torch.cuda.current_device())
+        return dev
+
+    @torch.no_grad()
+    def score_host(self, kwd_features, utt_features, kwd_mask, utt_mask, hotword_mask=None, max_pairs: int = 256,
+                   threshold: Optional[float] = None, kwd_slab: int = 125, device=None, utt_slab: int = 16,
+                   kwd_bank: Optional[torch.Tensor] = None, kwd_len: Optional[torch.Tensor] = None):
+        """``score`` for inputs that live in (pinned) HOST memory -- what the reference's DataLoader hands to
+        ``test_step`` (model.py:749-765).  Phase 1: the keyword bank is uploaded slab by slab on a copy stream and
+        compressed into its resident fp16 form (``compress_host``; skipped when ``kwd_bank`` -- an already resident
+        compressed bank [C,K,Tk',Dk], e.g. ``bank.KeywordBank.kwd_n`` -- is given, ``kwd_features``/``kwd_mask`` may then
+        be None).  Phase 2: the utterances stream through in slabs of ``utt_slab``, each uploaded while the previous
+        one is compressed and scored against the whole bank.  Returns device tensors like ``score``."""
+        dev = self._b200_device(device)
+        K = kwd_bank.shape[1] if kwd_bank is not None else kwd_features.shape[0]
+        U = utt_features.shape[0]
+        if K == 0 or U == 0:
+            return _empty_scores(K, U, dev)
+        eng = self.prepare(dev)
+        layer_idx = list(self.b200_layer_idx) if self.b200_layer_idx is not None else list(range(self.hparams.n_layers))
+        kwd_n = kwd_bank if kwd_bank is not None else self.compress_host(kwd_features, kwd_mask, kwd_slab, dev, "kwd")
+        if kwd_len is None and kwd_bank is None and self.b200_ragged and kwd_mask is not None:
+            # lengths from the frame masks: a [K,C,T'] host tensor, small next to the embeddings
+            kwd_len = KWSEngine.keyword_lengths(kwd_mask.to(dev, non_blocking=True))
+        hot = hotword_mask.to(dev, non_blocking=True) if hotword_mask is not None else None
+        logits = torch.empty((K, U, 2), dtype=torch.float32, device=dev)
+        lowp = self.b200_body_dtype != "float32"
+        out_mode = ops.STEM_OUT_NHWC_BF16 if lowp else ops.STEM_OUT_NCHW_F32
+        bufs = self._stage.setdefault("bufs", {}) if getattr(self, "_stage", None) is not None else {}
+        for us, ms, u0, u1 in self._host_slabs("utt", utt_features, utt_mask, utt_slab, dev):
+            utt_n = eng.compress(us, ms, layer_idx)
+
+            def consume(a0, a1, b0, b1, st, u0=u0):
+                logits[a0:a1, u0 + b0:u0 + b1] = self._body(st).float().view(a1 - a0, b1 - b0, 2)
+
+            eng.hot_path(kwd_n, utt_n, out_mode, max_pairs, consume, bufs=bufs, kwd_len=kwd_len)
         hw = None
         if hot is not None:
             hw = hot.to(torch.float32).view(K, 1).expand(K, U).contiguous().view(-1)
@@ -389,7 +435,7 @@ class B200ForwardMixin:
 
     @torch.no_grad()
     def score_compressed(self, kwd_n, utt_n, hotword_mask=None, max_pairs: int = 256,
-                         threshold: Optional[float] = None):
+                         threshold: Optional[float] = None, kwd_len: Optional[torch.Tensor] = None):
         eng = self.prepare(kwd_n.device)
         K, U = kwd_n.shape[1], utt_n.shape[1]
         logits = torch.empty((K, U, 2), dtype=torch.float32, device=kwd_n.device)
@@ -398,7 +444,8 @@ class B200ForwardMixin:
         def consume(k0, k1, u0, u1, st):
             logits[k0:k1, u0:u1] = self._body(st).float().view(k1 - k0, u1 - u0, 2)
 
-        eng.hot_path(kwd_n, utt_n, ops.STEM_OUT_NHWC_BF16 if lowp else ops.STEM_OUT_NCHW_F32, max_pairs, consume)
+        eng.hot_path(kwd_n, utt_n, ops.STEM_OUT_NHWC_BF16 if lowp else ops.STEM_OUT_NCHW_F32, max_pairs, consume,
+                     kwd_len=kwd_len if self.b200_ragged else None)
         hw = None
         if hotword_mask is not None:
             hw = hotword_mask.to(logits.device, torch.float32).view(K, 1).expand(K, U).contiguous().view(-1)

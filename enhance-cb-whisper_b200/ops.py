@@ -292,12 +292,15 @@ def sim_stem_supported(Cc: int, Tk: int, Tu: int, Dk: int, out_mode: int = STEM_
 @_guard
 def sim_stem(kwd_n: torch.Tensor, utt_n: torch.Tensor, w_fused: torch.Tensor, bias: torch.Tensor, out_mode: int,
              diag: bool = False, out: Optional[torch.Tensor] = None, k_range: Optional[Tuple[int, int]] = None,
-             u_range: Optional[Tuple[int, int]] = None, per_keyword: bool = False) -> torch.Tensor:
+             u_range: Optional[Tuple[int, int]] = None, per_keyword: bool = False,
+             kwd_len: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Fused similarity + stem (w_fused from pack_stem_fused).  kwd_n fp16 [C,K,Tk,Dk], utt_n fp16 [C,U,Tu,Dk] -> stem activation of the
     pairs of keywords k_range=(k0,k1) x utterances u_range=(u0,u1) (default: all), pair = (k-k0)*(u1-u0) + (u-u0)
     (DIAG: pair = k-k0): NCHW fp32 [N,64,Ho,Wo] or channels_last bf16.  ``out`` may be a larger reused
     buffer (its first N pairs are written).  ``per_keyword``: utt_n is [C, K*U, Tu, Dk], one utterance-side operand
-    per (keyword, utterance) (config #4: the native-resolution similarity, contracted with the resize's height map)."""
+    per (keyword, utterance) (config #4: the native-resolution similarity, contracted with the resize's height map).
+    ``kwd_len``: int32 [K] valid frames per keyword (frames beyond are zero rows of kwd_n): output rows beyond a
+    keyword are filled with relu(bias) without similarity / stem work -- bit-identical output (kws_sim_stem_ragged)."""
     lib = _lib.load()
     Cc, K, Tk, Dk = kwd_n.shape
     Cu, U, Tu, Dku = utt_n.shape
@@ -319,7 +322,10 @@ def sim_stem(kwd_n: torch.Tensor, utt_n: torch.Tensor, w_fused: torch.Tensor, bi
         want = torch.float32 if f32 else torch.bfloat16
         if out.dtype != want or out.numel() < pairs * 64 * Ho * Wo:
             raise KWSError(f"out buffer too small / wrong dtype for {pairs} pairs")
-    check(lib.kws_sim_stem_range(_cuda(kwd_n, "kwd_n", torch.float16), _cuda(utt_n, "utt_n", torch.float16), Cc, K,
+    if kwd_len is not None and (kwd_len.dtype != torch.int32 or kwd_len.numel() != K):
+        raise KWSError(f"kwd_len must be int32 [K={K}]")
+    check(lib.kws_sim_stem_ragged(_cuda(kwd_n, "kwd_n", torch.float16), _cuda(utt_n, "utt_n", torch.float16),
+                                 _cuda(kwd_len, "kwd_len", torch.int32), Cc, K,
                                  U, Tk, Tu, Dk,
                                  PAIRS_PER_KEYWORD if per_keyword else (PAIRS_DIAG if diag else PAIRS_ALL), k0, k1 - k0,
                                  u0, u1 - u0,

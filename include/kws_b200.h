@@ -184,6 +184,16 @@ int kws_sim_stem_range(const void* kwd_n, const void* utt_n, int C, int K, int U
                        int pair_mode, int k0, int nk, int u0, int nu, const void* w_fused, const float* bias,
                        int out_mode, void* out, void* stream);
 
+/* The same with a keyword LENGTH TABLE (ragged keyword bank: real keywords are 10-60 of the 150 padded frames,
+ * src/efficient_kws/dataset.py:784-819).  kwd_len DEVICE int32 [K]: frames >= kwd_len[k] of keyword k are zero rows of
+ * kwd_n (the 0/1 frame mask folded in by the compression kernels guarantees it).  Output rows whose receptive field
+ * starts at or beyond kwd_len[k] are exactly relu(bias): the kernel skips their similarity and stem MMAs and fills
+ * them with the constant tile.  The output is bit-identical to kws_sim_stem_range; kwd_len == NULL is that call.
+ * Not with KWS_PAIRS_PER_KEYWORD. */
+int kws_sim_stem_ragged(const void* kwd_n, const void* utt_n, const int32_t* kwd_len, int C, int K, int U, int Tk, int Tu,
+                        int Dk, int pair_mode, int k0, int nk, int u0, int nu, const void* w_fused, const float* bias,
+                        int out_mode, void* out, void* stream);
+
 /* Config #4 (original CB-Whisper classifier): bilinear resize of the layer-wise similarity images of
  * ragged keywords to the classifier's fixed input size (replaces torchvision resize(..., antialias=False)
  * == F.interpolate(bilinear, align_corners=False), src/model/cb_whisper.py:208; dataset twin

@@ -40,4 +40,8 @@ def test_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["metric"] == "kwd_utt_pairs_per_s" and line["unit"] == "pairs/s"
     assert line["higher_is_better"] is True and line["value"] > 0 and line["gpu_launches"] == 0
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
-    assert line["e2e"] == {"value": line["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # like-for-like scopes (VERDICT r1 / ADVICE r1): `value` is the in-scope figure (the scope of the B200 arm's `value`),
+    # `e2e.value` the whole forward through logits (the scope of the B200 arm's `e2e.value`), which is slower
+    assert line["cpu_baseline"]["value"] == line["value"] and line["config"]["same_scope_as_b200_value"] is True
+    assert line["e2e"]["unit"] == "pairs/s" and line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert 0 < line["e2e"]["value"] < line["value"]

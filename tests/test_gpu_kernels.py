@@ -277,6 +277,53 @@ def test_sim_stem_range_is_a_block_of_the_full_job(ops, cuda_dev):
         ops.sim_stem(kn, un, wp, bias, ops.STEM_OUT_NCHW_F32, k_range=(5, 9))
 
 
+@pytest.mark.parametrize("Cc,K,U,Tk,Tu,Dk,modes", [
+    (12, 9, 3, 150, 300, 64, ("bf16", "f32")),   # the bench's instance (12 layers, Dk = 64), 16-row chunks
+    (3, 7, 2, 37, 130, 64, ("bf16", "f32")),     # generic 16-row instance
+    (4, 6, 2, 150, 200, 384, ("bf16", "f32")),   # L variant: 48-row chunks
+    (5, 6, 2, 75, 251, 128, ("bf16",)),          # 32-row chunks
+    (32, 5, 2, 75, 300, 64, ("bf16",)),          # multi-pass (12 + 12 + 8 layers)
+    (16, 40, 5, 30, 260, 64, ("bf16",)),         # multi-pass, more items than SMs
+])
+def test_sim_stem_ragged_is_bit_identical(ops, cuda_dev, Cc, K, U, Tk, Tu, Dk, modes):
+    """kws_sim_stem_ragged (keyword length table: rows beyond a keyword skipped and filled with relu(bias)) ==
+    kws_sim_stem_range on the same operands, bit for bit, for every row of a pre-poisoned output buffer; lengths
+    include 0 (ghost / empty), 1, odd / even, the full length and lengths above it."""
+    g = gen(cuda_dev)
+    kn = unit_rows(Cc, K, Tk, Dk, g=g, dev=cuda_dev).half()
+    un = unit_rows(Cc, U, Tu, Dk, g=g, dev=cuda_dev).half()
+    lens = torch.randint(0, Tk + 1, (K,), generator=g, device=cuda_dev, dtype=torch.int32)
+    lens[0], lens[1], lens[2], lens[3] = 0, 1, Tk, min(Tk, 2)
+    lens[4] = Tk - 1
+    for k in range(K):
+        kn[:, k, int(lens[k]):] = 0  # what the folded frame mask guarantees
+    lens_arg = lens.clone()
+    lens_arg[2] = Tk + 5  # clamped by the kernel
+    sd = {k: v.to(cuda_dev) for k, v in O.make_weights("L", Cc, 64, seed=17).items()}
+    wf, bias = pack_stem_fused(ops, sd)
+    Ho, Wo = (Tk + 1) // 2, (Tu + 1) // 2
+    for mode in modes:
+        om = ops.STEM_OUT_NHWC_BF16 if mode == "bf16" else ops.STEM_OUT_NCHW_F32
+        dt = torch.bfloat16 if mode == "bf16" else torch.float32
+        dense = ops.sim_stem(kn, un, wf, bias, om).clone()
+        buf = torch.full((K * U * 64 * Ho * Wo,), float("nan"), dtype=dt, device=cuda_dev)
+        rag = ops.sim_stem(kn, un, wf, bias, om, out=buf, kwd_len=lens_arg)
+        assert not torch.isnan(rag.float()).any(), "ragged kernel left output rows unwritten"
+        assert torch.equal(rag, dense)
+        # a sub-range of the pair grid (k0 > 0: the length table is indexed by the global keyword id)
+        buf.fill_(float("nan"))
+        blk = ops.sim_stem(kn, un, wf, bias, om, out=buf, k_range=(1, K - 1), u_range=(U - 1, U), kwd_len=lens_arg)
+        exp = dense.view(K, U, *dense.shape[1:])[1:K - 1, U - 1:U].flatten(0, 1)
+        assert torch.equal(blk, exp)
+    # rows beyond a keyword really are the constant relu(bias) tile
+    out = ops.sim_stem(kn, un, wf, bias, ops.STEM_OUT_NCHW_F32 if "f32" in modes else ops.STEM_OUT_NHWC_BF16, kwd_len=lens_arg)
+    o = out.view(K, U, *out.shape[1:]).float()
+    rb = torch.relu(bias)
+    if "f32" not in modes:
+        rb = rb.to(torch.bfloat16).float()
+    assert torch.equal(o[0], rb[None, :, None, None].expand_as(o[0]))  # length 0: the whole image
+
+
 # ---- max-pool that follows the stem -----------------------------------------------------------------
 @pytest.mark.parametrize("N,Cc,H,W", [(1, 64, 1, 1), (2, 64, 7, 9), (3, 64, 38, 375), (2, 64, 75, 750), (2, 8, 12, 5)])
 def test_maxpool_nhwc_is_bit_identical_to_torch(ops, cuda_dev, N, Cc, H, W):
