@@ -1,0 +1,92 @@
+"""GPU, NCCL, world_size 2 (skipped below two devices): the keyword-sharded scoring path on hardware --
+sharded + gathered scores == the single-GPU scores bit for bit, distributed top-k == single-device top-k of the
+full matrix (consumers: model.py:523 torch.topk, :783-795 scores)."""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, variant, q):
+    import torch.distributed as dist
+
+    import enhance_cb_whisper_b200 as kb
+    from enhance_cb_whisper_b200 import ops, parallel
+    from oracle import kws_oracle as O
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        torch.backends.cudnn.benchmark = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        C, D, P, Tk, Tu, K, U = 3, 128, 64, 22, 70, 12, 3  # shards of 6 keywords
+        torch.manual_seed(7)  # same body + head on every rank
+        m = kb.KWSModelB200(n_layers=C, embedding_dim=D, proj_mlp_units=P, learn_features=variant != "L",
+                            proj_mlp=variant != "L", frames_conv=variant == "LEF", resnet_version="resnet-18",
+                            features_size=(Tk, Tu), threshold=0.5)
+        sd = dict(m.state_dict())
+        sd.update(O.make_weights(variant, C, D, P, seed=5))
+        m.load_state_dict(sd)
+        m = m.to(dev).eval()
+        kwd, utt, km, um, hot = O.make_inputs(K, U, C, D, Tk, Tu, seed=6, ghost_frac=0.2)
+        kwd[7] = kwd[2]  # identical keywords on different ranks: exact score ties across the shard boundary
+        km[7], hot[7] = km[2], hot[2]
+        if variant == "LEF":
+            km, um = O.pooled_mask(km).contiguous(), O.pooled_mask(um).contiguous()
+        kwd, utt, km, um, hot = (t.to(dev) for t in (kwd, utt, km, um, hot))
+        lo, hi = parallel.shard_range(K, world, rank)
+        # max_pairs = 3: blocks of 3 keywords x 1 utterance in the sharded AND in the single-GPU job, so that the
+        # library convolutions of the body see identical batches (their algorithm choice depends on the batch size)
+        sc_l, det_l, _ = m.score(kwd[lo:hi].contiguous(), utt, km[lo:hi].contiguous(), um, hotword_mask=hot[lo:hi],
+                                 max_pairs=3)
+        gathered = parallel.gather_scores(sc_l, K)
+        det_g = parallel.gather_scores(det_l.float(), K).to(torch.uint8)
+        tv, ti = parallel.distributed_topk(sc_l, 5, K, ops.topk)
+        sc_1, det_1, _ = m.score(kwd, utt, km, um, hotword_mask=hot, max_pairs=3)  # the whole job on this GPU alone
+        ev, ei = ops.topk(sc_1.contiguous(), 5)
+        q.put((rank, bool(torch.equal(gathered, sc_1)), bool(torch.equal(det_g, det_1)), bool(torch.equal(tv, ev)),
+               bool(torch.equal(ti, ei)), bool(torch.equal(sc_1[7], sc_1[2])),
+               f"max |gathered - single| {float((gathered - sc_1).abs().max()):.3e}; top-k ids {ti.tolist()} vs {ei.tolist()}"))
+    except Exception as exc:  # surface the worker's error in the parent's assertion message
+        import traceback
+
+        q.put((rank, False, False, False, False, False, "worker failed: " + "".join(traceback.format_exception(exc))[-1500:]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("variant", ["LE", "LEF"])
+def test_sharded_scores_and_topk_equal_single_gpu(built_lib, variant):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, variant, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, sc_ok, det_ok, tv_ok, ti_ok, tie, info in res:
+        assert tie, f"test set-up: the duplicated keyword should score identically ({info})"
+        assert sc_ok and det_ok, f"rank {rank}: gathered scores / detections differ from the single-GPU job ({info})"
+        assert tv_ok and ti_ok, f"rank {rank}: distributed top-k differs from the single-device top-k ({info})"
