@@ -37,6 +37,8 @@ SIGNATURES = {
     "kws_normalize_rows": (_i, [_vp, _i, _i, _i, _i, C.POINTER(C.c_int32), _i, _vp, _f, _vp, _vp]),
     "kws_cast_rows16": (_i, [_vp, _i, _i, _i, _i, C.POINTER(C.c_int32), _i, _i, _vp, _vp]),
     "kws_mlp": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp]),
+    "kws_mlp_fused": (_i, [_vp, _i, _i, _i, _i, C.POINTER(C.c_int32), _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp]),
+    "kws_mlp_fused_supported": (_i, [_i, _i, _i]),
     "kws_temporal": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp, _vp]),
     "kws_sim": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "kws_stem": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),

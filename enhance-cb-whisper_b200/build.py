@@ -23,7 +23,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libkws_b200.so")
 LIB_DBG = os.path.join(HERE, "libkws_b200_dbg.so")
 OBJ_DIR = os.path.join(HERE, "build")
-SOURCES = ["kws_abi.cu", "kws_prep.cu", "kws_gemm.cu", "kws_temporal.cu", "kws_stem.cu", "kws_fused.cu"]
+SOURCES = ["kws_abi.cu", "kws_prep.cu", "kws_gemm.cu", "kws_mlp_fused.cu", "kws_temporal.cu", "kws_stem.cu", "kws_fused.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

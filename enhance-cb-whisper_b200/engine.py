@@ -82,9 +82,10 @@ def pack_weights(sd: Mapping[str, torch.Tensor], variant: str, C: int, D: int, P
 class KWSEngine:
     """compress / similarity / stem over batches, with bounded workspaces."""
 
-    def __init__(self, weights: PackedWeights, workspace_bytes: int = 8 << 30):
+    def __init__(self, weights: PackedWeights, workspace_bytes: int = 8 << 30, fused_mlp: bool = True):
         self.w = weights
         self.workspace_bytes = int(workspace_bytes)
+        self.fused_mlp = bool(fused_mlp)  # kws_mlp_fused where the shape allows; False: kws_cast_rows16 + kws_mlp
 
     # -- stage 1: per-layer compression -> normalised fp16 operands [C,B,T',Dk] ------
     def out_frames(self, T: int) -> int:
@@ -115,8 +116,14 @@ class KWSEngine:
         if w.variant == "L":
             return ops.normalize_rows(x, layer_idx, mask)
         T2 = self.out_frames(T)
-        out = torch.empty((w.C, B, T2, w.P), dtype=torch.float16, device=x.device)
         H = w.w1.shape[1]
+        if self.fused_mlp and ops.mlp_fused_supported(D, H, w.P):
+            # one kernel from the raw fp32 rows to the compressed operands: no 16-bit copy of x, no hidden tensor
+            if w.variant == "LE":
+                return ops.mlp_fused(x, layer_idx, w.w1, w.b1, w.w2, w.b2, mask, ops.MLP_OUT_NORM_F16)
+            proj = ops.mlp_fused(x, layer_idx, w.w1, w.b1, w.w2, w.b2, None, ops.MLP_OUT_RAW_16)
+            return ops.temporal(proj, w.wt, w.bt, mask)
+        out = torch.empty((w.C, B, T2, w.P), dtype=torch.float16, device=x.device)
         per_item = w.C * T * (D + H) * 2 + w.C * T * w.P * 2
         step = max(1, min(B, self.workspace_bytes // max(per_item, 1)))
         for b0 in range(0, B, step):

@@ -203,6 +203,36 @@ def mlp(x16: torch.Tensor, B: int, T: int, w1: torch.Tensor, b1: torch.Tensor, w
     return out
 
 
+def mlp_fused_supported(D: int, H: int, P: int) -> bool:
+    return bool(_lib.load().kws_mlp_fused_supported(int(D), int(H), int(P)))
+
+
+@_guard
+def mlp_fused(x: torch.Tensor, layer_idx: Sequence[int], w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor,
+              b2: torch.Tensor, mask: Optional[torch.Tensor], out_mode: int, eps: float = SIM_EPS) -> torch.Tensor:
+    """The per-layer projector as one kernel on the raw embeddings: x fp32 [B,Cin,T,D] (+ layer selection) ->
+    fp16 [C,B,T,P] (normalised * mask), fp32 (raw) or the weights' 16-bit type (raw, feeds temporal).  w1 [C,H,D],
+    w2 [C,P,H] fp16 or bf16.  The hidden activation never reaches HBM (kws_mlp_fused)."""
+    lib = _lib.load()
+    B, Cin, T, D = x.shape
+    Cc = len(layer_idx)
+    dt = w1.dtype
+    if dt not in (torch.float16, torch.bfloat16) or w2.dtype != dt:
+        raise KWSError(f"w1/w2 must share one 16-bit dtype, got {w1.dtype}/{w2.dtype}")
+    H, P = w1.shape[1], w2.shape[1]
+    if tuple(w1.shape) != (Cc, H, D) or tuple(w2.shape) != (Cc, P, H):
+        raise KWSError("projector weight shapes do not match x / layer_idx")
+    if mask is not None and tuple(mask.shape) != (B, Cc, T):
+        raise KWSError(f"mask must be [B,C,T]=({B},{Cc},{T}), got {tuple(mask.shape)}")
+    out_dt = {MLP_OUT_NORM_F16: torch.float16, MLP_OUT_RAW_F32: torch.float32, MLP_OUT_RAW_16: dt}[out_mode]
+    out = torch.empty((Cc, B, T, P), dtype=out_dt, device=x.device)
+    check(lib.kws_mlp_fused(_cuda(x, "x", torch.float32), B, Cin, T, D, _layers(layer_idx), Cc, H, P,
+                            F16 if dt == torch.float16 else BF16, _cuda(w1, "w1", dt), _cuda(b1, "b1", torch.float32),
+                            _cuda(w2, "w2", dt), _cuda(b2, "b2", torch.float32), _cuda(mask, "mask", torch.float32),
+                            eps, out_mode, _cuda(out, "out"), _stream()), "kws_mlp_fused")
+    return out
+
+
 @_guard
 def temporal(proj16: torch.Tensor, w16: torch.Tensor, bf: torch.Tensor, mask: Optional[torch.Tensor],
              eps: float = SIM_EPS) -> torch.Tensor:

@@ -128,6 +128,19 @@ int kws_mlp(const void* x16, int C, int B, int T, int D, int H, int P, int dtype
             const float* b1, const void* w2_16, const float* b2, void* hidden16, const float* mask, float eps,
             int out_mode, void* out, void* stream);
 
+/* The same projector as ONE kernel, fed by the raw fp32 embeddings: layer selection (dataset.py:570-573), fp32 -> 16-bit
+ * cast, Linear(D,H) + ReLU, Linear(H,P) and the normalise * mask epilogue (model.py:92-104, :146-150, :214-216,
+ * :187-191) fused; the hidden activation stays in tensor / shared memory and x is read once (H <= 384; twice from L2
+ * for larger H, which run as two hidden passes).  Replaces kws_cast_rows16 + kws_mlp.
+ *   x fp32 [B,Cin,T,D]; layer_idx HOST int32 [C]; w1 [C,H,D], w2 [C,P,H] of the 16-bit type dtype16; b1 fp32 [C,H],
+ *   b2 fp32 [C,P]; mask fp32 [B,C,T] or NULL (KWS_MLP_OUT_NORM_F16 only); out [C, B*T, P] as kws_mlp's out_mode.
+ *   kws_mlp_fused_supported(D,H,P) == 1: D % 64 == 0, H % 64 == 0 and H = n * NH with NH <= 384 a multiple of 64
+ *   (n <= 4), P % 16 == 0, P <= 64, and the stages fit 227 KB of shared memory; otherwise use the two-call form. */
+int kws_mlp_fused(const float* x, int B, int Cin, int T, int D, const int32_t* layer_idx, int C, int H, int P,
+                  int dtype16, const void* w1_16, const float* b1, const void* w2_16, const float* b2, const float* mask,
+                  float eps, int out_mode, void* out, void* stream);
+int kws_mlp_fused_supported(int D, int H, int P);
+
 /* LEF temporal projector (BN folded) + MaxPool1d(3,2,1) + L2 normalisation +
  * mask folding (model.py:107-124, :152-166, :214-216, :187-191) as a tcgen05 implicit GEMM over the
  * frame axis (three taps = one shared-memory tile read at three row offsets).

@@ -129,6 +129,52 @@ def test_mlp_matches_same_quantisation_reference(ops, cuda_dev, Cc, B, T, D, P, 
     assert maxerr(raw, ef) <= (2e-2 if d16 == "BF16" else 5e-3)
 
 
+@pytest.mark.parametrize("Cc,Cin,B,T,D,P,d16", [
+    (2, 2, 3, 50, 128, 64, "F16"),      # H = 64: one 64-column hidden block
+    (3, 5, 2, 150, 768, 64, "F16"),     # cfg2 shape: H = 384 in one pass, two MMAs per k-step; layer selection
+    (1, 1, 2, 7, 1280, 64, "F16"),      # cfg3 shape: H = 640 as two passes of 320
+    (2, 3, 1, 131, 1024, 64, "BF16"),   # whisper-medium: H = 512 as two passes of 256; bf16 operands
+    (1, 1, 1, 300, 256, 32, "F16"),     # P = 32
+    (12, 12, 20, 150, 256, 64, "F16"),  # 288 work items on 148 persistent CTAs, 12 layer changes (W2 reloads)
+    (2, 2, 1, 1, 512, 16, "F16"),       # a single row, P = 16
+])
+def test_mlp_fused_matches_two_call_path_and_reference(ops, cuda_dev, Cc, Cin, B, T, D, P, d16):
+    """kws_mlp_fused (raw fp32 rows -> cast -> GEMM1 -> ReLU -> GEMM2 -> normalise * mask in one kernel, hidden on chip)
+    against kws_cast_rows16 + kws_mlp (same quantisation points: 16-bit x, 16-bit hidden) and against torch on the
+    same quantised operands; all three output modes."""
+    g = gen(cuda_dev)
+    code = getattr(ops, d16)
+    tdt = ops.TORCH16[code]
+    H = D // 2
+    assert ops.mlp_fused_supported(D, H, P)
+    x = unit_rows(B, Cin, T, D, g=g, dev=cuda_dev)
+    lidx = list(range(Cin))[::-1][:Cc]
+    w1 = torch.randn(Cc, H, D, generator=g, device=cuda_dev) * (4.0 / D ** 0.5)
+    b1 = torch.randn(Cc, H, generator=g, device=cuda_dev) * 0.05
+    w2 = torch.randn(Cc, P, H, generator=g, device=cuda_dev) / H ** 0.5
+    b2 = torch.randn(Cc, P, generator=g, device=cuda_dev) * 0.05
+    mask = (torch.rand(B, Cc, T, generator=g, device=cuda_dev) > 0.1).float()
+    w1b, w2b = ops.cast16(w1, code), ops.cast16(w2, code)
+    xb = ops.cast_rows16(x, lidx, code)
+    xq = xb.float().view(Cc, B, T, D)
+    h = torch.relu(torch.einsum("cbtd,chd->cbth", xq, w1b.float()) + b1[:, None, None, :]).to(tdt).float()
+    exp = torch.einsum("cbth,cph->cbtp", h, w2b.float()) + b2[:, None, None, :]
+    expn = exp / exp.norm(dim=-1, keepdim=True).clamp(min=1e-6) * mask.permute(1, 0, 2)[..., None]
+    raw = ops.mlp_fused(x, lidx, w1b, b1, w2b, b2, None, ops.MLP_OUT_RAW_F32)
+    assert raw.shape == (Cc, B, T, P) and raw.dtype == torch.float32
+    assert maxerr(raw, exp) <= 2e-3
+    nrm = ops.mlp_fused(x, lidx, w1b, b1, w2b, b2, mask, ops.MLP_OUT_NORM_F16)
+    assert nrm.dtype == torch.float16 and maxerr(nrm, expn) <= 2e-3
+    r16 = ops.mlp_fused(x, lidx, w1b, b1, w2b, b2, None, ops.MLP_OUT_RAW_16)
+    assert r16.dtype == tdt and maxerr(r16, exp) <= (3e-2 if d16 == "BF16" else 4e-3)
+    # the two-call path quantises at the same points and accumulates in the same order
+    raw2 = ops.mlp(xb, B, T, w1b, b1, w2b, b2, None, ops.MLP_OUT_RAW_F32)
+    nrm2 = ops.mlp(xb, B, T, w1b, b1, w2b, b2, mask, ops.MLP_OUT_NORM_F16)
+    assert maxerr(raw, raw2) <= 1e-5 and maxerr(nrm, nrm2) <= 1e-3
+    with pytest.raises(Exception):  # a mask of another shape is refused, not mis-indexed
+        ops.mlp_fused(x, lidx, w1b, b1, w2b, b2, mask[:, :, :-1].contiguous() if T > 1 else mask[:, :1, :0], ops.MLP_OUT_NORM_F16)
+
+
 # ---- LEF temporal projector -------------------------------------------------------------------
 @pytest.mark.parametrize("d16", ["F16", "BF16"])
 @pytest.mark.parametrize("Cc,B,T,P", [(2, 3, 23, 64), (3, 2, 150, 64), (1, 1, 71, 32), (1, 2, 1, 64), (1, 1, 2, 64),
