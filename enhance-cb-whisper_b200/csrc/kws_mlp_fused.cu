@@ -83,7 +83,7 @@ kws_mlp_fused_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_co
   uint64_t* out_full = hempty + 2;   // GEMM2 of an item complete -> epilogue
   uint64_t* out_empty = out_full + 1;  // epilogue has read the output accumulator (4 warp arrivals) -> MMA
   uint64_t* w2_full = out_empty + 1;   // W2 of the item's layer resident (TMA tx) -> MMA
-  uint64_t* w2_free = w2_full + 1;     // all GEMM2 MMAs of an item complete (commit) -> TMA may overwrite W2
+  uint64_t* w2_free = w2_full + 1;     // all GEMM2 MMAs of a layer's items complete (commit) -> TMA may overwrite W2
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w2_free + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -128,12 +128,15 @@ kws_mlp_fused_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_co
     // ===================== TMA producer: W1 k-blocks per stage, W2 per layer change =====================
     if (elect_one()) {
       int stage = 0;
-      uint32_t phase = 0, seq = 0;
+      uint32_t phase = 0, nchg = 0;  // nchg: W2 loads issued = layer changes seen by this CTA
       int prev_c = -1;
-      for (long long it = blockIdx.x; it < p.num_items; it += gridDim.x, ++seq) {
+      for (long long it = blockIdx.x; it < p.num_items; it += gridDim.x) {
         const int c = (int)(it / p.m_tiles);
         if (c != prev_c) {
-          if (seq > 0) mbar_wait(w2_free, (seq - 1) & 1, 900);  // the previous item's GEMM2 no longer reads W2
+          // w2_free completes one phase per layer change (committed by the MMA issuer after the last item of a layer),
+          // so producer and issuer stay in lock-step on it whatever the run-ahead of the W1 pipeline
+          if (nchg > 0) mbar_wait(w2_free, (nchg - 1) & 1, 900);  // the previous layer's GEMM2s no longer read W2
+          ++nchg;
           mbar_arrive_expect_tx(w2_full, (uint32_t)((p.H / 64) * p.P * 128));
           for (int j = 0; j < p.H / 64; ++j) tma_load_3d(&map_w2, w2_full, s_w2 + j * p.P * 128, j * 64, 0, c);
           prev_c = c;
@@ -206,7 +209,8 @@ kws_mlp_fused_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_co
           }
         }
         umma_commit(out_full);
-        umma_commit(w2_free);
+        const long long nit = it + gridDim.x;
+        if (nit >= p.num_items || (int)(nit / p.m_tiles) != c) umma_commit(w2_free);  // last item of this layer here
       }
     }
     __syncwarp();
