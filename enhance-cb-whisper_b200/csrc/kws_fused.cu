@@ -75,6 +75,12 @@
   } while (0)
 #endif
 
+#ifdef KWS_DEBUG_HOOKS
+#define KWS_WHATIF(bit) ((p.whatif & (bit)) != 0)
+#else
+#define KWS_WHATIF(bit) false
+#endif
+
 namespace kws {
 
 constexpr int G_THREADS = 384;
@@ -125,6 +131,9 @@ struct FusedParams {
   const int32_t* kwd_len;  // optional [K]: valid frames of every keyword (rows >= len are zero in kwd_n); output rows whose
                            // receptive field lies beyond are relu(bias): no similarity, no stem MMAs, constant fill
   long long num_items;
+  int whatif;    // development what-if switches (KWS_DEBUG_HOOKS builds only; results are WRONG when set): 1 epilogue
+                 // releases the accumulator at once and does nothing else | 2 no half-b shift (no mailbox, no shuffles) |
+                 // 4 no TMA store | 8 stem issues kernel row 0 only | 16 similarity issues one of four k-steps
   long long* dbg;  // optional [grid][16] cycle counters (issuer 0-4, epilogue 5-7, converter 8-11; development aid), or null
 };
 
@@ -407,8 +416,10 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
             const uint64_t adesc = sdesc0 + (uint64_t)(sa >> 4);
             const uint64_t bdesc = adesc + (uint64_t)(G_A_BYTES >> 4);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
+            for (int k = 0; k < 4; ++k) {
+              if (KWS_WHATIF(16) && k > 0) break;
               umma_f16(d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc_sim, (kb | k) != 0);
+            }
             umma_commit(&oempty[o_stage]);
             KWS_TRACE(3, tr_s, 5);
             ++tr_s;
@@ -472,6 +483,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
               KWS_TRACE(0, acc_seq, 5);
               tc_fence_after();
             }
+            if (KWS_WHATIF(8) && di != 0 && di != 3) continue;
             const uint32_t slot0 = (slot_base + (di >> 1)) & (G_NR - 1);
             // block [k8][rp][plane]: rp = (di+1)&1; byte offsets in 16-byte units
             const uint32_t row16 = ((((di + 1) & 1) * 2 * G_BLOCK) >> 4) + slot0 * 64;
@@ -572,6 +584,11 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
         if (warp == 4 && lane == 0) KWS_TRACE(1, acc_seq, 0);
         te_wait += e1 - e0;
         tc_fence_after();
+        if (KWS_WHATIF(1)) {
+          tc_fence_before();
+          mbar_arrive(&aempty[acc]);
+          continue;
+        }
         const uint32_t t_row = tmem_base + acc * G_ACC_COLS + ((uint32_t)(q * 32) << 16);
         const int oi = 2 * P + row_sel;
         const bool ok = col_ok && oi < p.Ho;
@@ -637,6 +654,8 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
             te_ld += KWS_CLK() - e1;
           }
           float* mbox = (grp & 1) == 0 ? mbox0 : mbox1;
+          long long f1 = f0;
+          if (!KWS_WHATIF(2)) {
           if (!lo_warp && lane < 2) {
             float4* dst = reinterpret_cast<float4*>(mbox + lane * 32);
 #pragma unroll
@@ -647,7 +666,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
                                                     __uint_as_float(vb[h][e + 2]), __uint_as_float(vb[h][e + 3]));
           }
           named_bar_sync(1 + row_sel, 64);  // mailbox written (and the other mailbox has been read)
-          const long long f1 = KWS_CLK();
+          f1 = KWS_CLK();
 #pragma unroll
           for (int h = 0; h < NH; ++h)
 #pragma unroll
@@ -662,6 +681,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
                 vb[h][e] = __float_as_uint(f.x), vb[h][e + 1] = __float_as_uint(f.y);
                 vb[h][e + 2] = __float_as_uint(f.z), vb[h][e + 3] = __float_as_uint(f.w);
               }
+          }
           }
 #pragma unroll
           for (int h = 0; h < NH; ++h) {
@@ -731,7 +751,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
           if (MULTI && loads_prev && tile_ok) ++pl_seq[set];
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0 && tile_ok) {
+          if (lane == 0 && tile_ok && !KWS_WHATIF(4)) {
             if (MULTI && p.acc_mode == 2 && p.reduce_mid) {
               // out (fp16 partial sums of the earlier passes) += this pass's partial sums, added where the data lives
               asm volatile(
@@ -1002,6 +1022,7 @@ static long long* g_fused_dbg = nullptr;
 static constexpr long long* g_fused_dbg = nullptr;
 #endif
 KWS_KNOB g_fused_grid_limit = 0;
+KWS_KNOB g_fused_whatif = 0;
 KWS_KNOB g_fused_rows = 0;
 KWS_KNOB g_fused_s12 = 1;  // 12-layer / Dk = 64 compile-time specialisation
 static int fused_n_mma(int C) { return C <= 8 ? 2 : 3; }
@@ -1019,6 +1040,7 @@ KWS_KNOB g_multi_prefetch = 2;
 KWS_KNOB g_multi_reduce = 1;       // middle passes: TMA reduce-add store (1) | load + add + store (0)
 KWS_KNOB g_multi_small_first = 0;  // remainder group first (no measurable difference; kept as a variant)
 #ifdef KWS_DEBUG_HOOKS
+extern "C" void kws_debug_set_fused_whatif(int bits) { g_fused_whatif = bits; }
 extern "C" void kws_debug_set_fused_s12(int on) { g_fused_s12 = on ? 1 : 0; }
 // force the similarity chunk height (16 | 32 | 48) instead of choosing it from the layer count
 extern "C" void kws_debug_set_fused_rows(int rows) { g_fused_rows = rows; }
@@ -1191,6 +1213,7 @@ extern "C" int kws_sim_stem_ragged(const void* kwd_n, const void* utt_n, const i
   if (grid > sms) grid = sms;
   if (g_fused_grid_limit > 0 && grid > g_fused_grid_limit) grid = g_fused_grid_limit;
   p.dbg = g_fused_dbg;
+  p.whatif = g_fused_whatif;
   p.kwd_len = kwd_len;
   const int n_groups = fused_groups(C);
   const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(w_fused);

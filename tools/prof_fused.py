@@ -1,0 +1,75 @@
+"""One launch set of a shipped fused-kernel instance (for `ncu --set full` and quick timings; not a benchmark).
+
+    python tools/prof_fused.py cfg2|cfg1|cfg3|mlp2|mlp3 [--pairs-k 74] [--utts 2] [--iters 2]
+
+cfg2: C=12, Dk=64, 150x1500  -> kws_fused_kernel<1,16,0,2,1>            (LE, the bench's headline instance)
+cfg1: C=4,  Dk=384, 150x1500 -> kws_fused_kernel<1,48,0,2,0>            (L variant)
+cfg3: C=32, Dk=64, 75x750    -> kws_fused_kernel<1,16,1,2,1> x2 + <1,16,1,2,0>  (LEF, multi-pass 12+12+8)
+mlp2 / mlp3: the fused per-layer projector (kws_mlp_fused) at D=768 / D=1280 on [K,12|32,150,D] keyword rows.
+148-pair launches: the bounded mbarrier waits trap under `--set full` on launches longer than ~10 ms.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from enhance_cb_whisper_b200 import ops  # noqa: E402
+
+SHAPES = {"cfg2": (12, 64, 150, 1500), "cfg1": (4, 384, 150, 1500), "cfg3": (32, 64, 75, 750)}
+
+
+def timeit(fn, n):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what", choices=sorted(SHAPES) + ["mlp2", "mlp3"])
+    ap.add_argument("--pairs-k", type=int, default=74)
+    ap.add_argument("--utts", type=int, default=2)
+    ap.add_argument("--iters", type=int, default=2)
+    a = ap.parse_args()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(7)
+    unit = lambda *s: torch.nn.functional.normalize(torch.randn(*s, generator=g, device=dev), dim=-1)
+    if a.what.startswith("mlp"):
+        Cc, D, P, T, K = (12, 768, 64, 150, a.pairs_k) if a.what == "mlp2" else (32, 1280, 64, 150, a.pairs_k)
+        H = D // 2
+        x = unit(K, Cc, T, D)
+        w1 = ops.cast16(torch.randn(Cc, H, D, generator=g, device=dev) / D ** 0.5)
+        w2 = ops.cast16(torch.randn(Cc, P, H, generator=g, device=dev) / H ** 0.5)
+        b1 = torch.randn(Cc, H, generator=g, device=dev) * 0.1
+        b2 = torch.randn(Cc, P, generator=g, device=dev) * 0.1
+        mask = torch.ones(K, Cc, T, device=dev)
+        t = timeit(lambda: ops.mlp_fused(x, list(range(Cc)), w1, b1, w2, b2, mask, ops.MLP_OUT_NORM_F16), a.iters)
+        fl = 2.0 * Cc * K * T * (D * H + H * P)
+        by = x.numel() * 4 + Cc * K * T * P * 2
+        print(f"mlp_fused {K}x{Cc}x{T}x{D}: {t:.3f} ms -> {fl / t / 1e9:.1f} TFLOP/s, {by / t / 1e6:.0f} GB/s")
+        return
+    Cc, Dk, Tk, Tu = SHAPES[a.what]
+    K, U = a.pairs_k, a.utts
+    Ho, Wo = (Tk + 1) // 2, (Tu + 1) // 2
+    kn, un = unit(Cc, K, Tk, Dk).half(), unit(Cc, U, Tu, Dk).half()
+    one, zero = torch.ones(64, device=dev), torch.zeros(64, device=dev)
+    wp, bias = ops.pack_stem_fused(torch.randn(64, Cc, 7, 7, generator=g, device=dev) * 0.05, one, zero, zero, one)
+    out = torch.empty(K * U, Ho, Wo, 64, dtype=torch.bfloat16, device=dev)
+    t = timeit(lambda: ops.sim_stem(kn, un, wp, bias, ops.STEM_OUT_NHWC_BF16, out=out), a.iters)
+    fl = (2.0 * 64 * 49 * Cc * Ho * Wo + 2.0 * Cc * Tk * Tu * Dk) * K * U
+    print(f"fused {a.what} C={Cc} Dk={Dk} {Tk}x{Tu}, {K * U} pairs: {t:.3f} ms -> {K * U / t * 1e3:.0f} pairs/s, "
+          f"{fl / t / 1e9:.1f} TFLOP/s algorithmic ({fl / t / 1e9 / 1364.9:.3f} of sustained)")
+
+
+if __name__ == "__main__":
+    main()
