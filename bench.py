@@ -548,8 +548,10 @@ def gen_inputs(ctx, wl, K, U, kw_seed=None):
             "klen": kmask_t.sum(dim=1).to(ctx.torch.int32)}
 
 
-def in_scope_record(ctx, wl, wl_name, model, data, steps, warmup, max_pairs, sampler=None, ragged=False):
-    """compression of the raw embeddings + fused similarity+stem over all pairs -> stem activation in HBM."""
+def in_scope_record(ctx, wl, wl_name, model, data, steps, warmup, max_pairs, sampler=None, ragged=False, end="stem"):
+    """compression of the raw embeddings + fused similarity+stem over all pairs -> stem activation in HBM.
+    ``end``: "stem" (the headline scope) | "pool_fused" (-> max-pooled activation, kws_sim_stem_pool: the stem
+    activation never reaches HBM) | "pool_separate" (-> the same tensor via stem activation + kws_maxpool_nhwc)."""
     import torch
 
     from enhance_cb_whisper_b200 import ops
@@ -574,7 +576,14 @@ def in_scope_record(ctx, wl, wl_name, model, data, steps, warmup, max_pairs, sam
         utt_n = eng.compress(data["utt"], data["umask"], layer_idx)
         if record:
             ev[2].record()
-        eng.hot_path(kwd_n, utt_n, ops.STEM_OUT_NHWC_BF16, max_pairs, None, bufs, launch_events if record else None,
+        if end == "pool_separate":
+            def pool_it(k0, k1, u0, u1, st):
+                n = st.shape[0] * 64 * ((st.shape[2] + 1) // 2) * ((st.shape[3] + 1) // 2)
+                if "pooled" not in bufs or bufs["pooled"].numel() < n:
+                    bufs["pooled"] = torch.empty(n, dtype=torch.bfloat16, device=st.device)
+                ops.maxpool_nhwc(st, out=bufs["pooled"])
+        eng.hot_path(kwd_n, utt_n, ops.STEM_OUT_POOL_NHWC_BF16 if end == "pool_fused" else ops.STEM_OUT_NHWC_BF16,
+                     max_pairs, pool_it if end == "pool_separate" else None, bufs, launch_events if record else None,
                      kwd_len=klen)
         if record:
             ev[3].record()
@@ -956,7 +965,7 @@ def run_b200_arm(args, wl_name):
     ctx = Ctx(args)
     torch = ctx.torch
     wl = WORKLOADS[wl_name]
-    only = set(args.only.split(",")) if args.only else {"main", "ragged", "e2e", "configs", "strong", "cpu"}
+    only = set(args.only.split(",")) if args.only else {"main", "ragged", "pool", "e2e", "configs", "strong", "cpu"}
     t_start = time.perf_counter()
     rank, world = ctx.rank, ctx.world
     line = {"metric": METRIC, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -1008,6 +1017,26 @@ def run_b200_arm(args, wl_name):
                       "kernel_ms_per_step": r["roofline"]["avg_launch_ms"] * r["roofline"]["launches"] / r["steps"]}
         except Exception as exc:
             ragged = {"value": None, "error": repr(exc)}
+    pooled = None
+    if "pool" in only and wl["variant"] != "CBW":
+        # SURVEY 8f row 3, measured: the same step ending at the MAX-POOLED activation (what ResNetEmbeddings hands to the
+        # encoder) -- fused into the similarity+stem kernel vs stem activation in HBM + the HBM-bound kws_maxpool_nhwc
+        try:
+            st, wu = max(1, min(args.steps, 3)), min(args.warmup, 3)
+            pf = in_scope_record(ctx, wl, wl_name, model, data, st, wu, args.max_pairs, end="pool_fused")
+            ps = in_scope_record(ctx, wl, wl_name, model, data, st, wu, args.max_pairs, end="pool_separate")
+            pooled = {"value": pf["value"], "unit": UNIT, "ms_per_step": pf["ms_per_step"], "steps": st,
+                      "kernel": "kws_fused_kernel<..., POOL> (kws_sim_stem_pool): stem activation never in HBM",
+                      "separate": {"value": ps["value"], "ms_per_step": ps["ms_per_step"],
+                                   "kernels": "kws_sim_stem (bf16 stem activation in HBM) + kws_maxpool_nhwc"},
+                      "speedup_vs_separate": pf["value"] / ps["value"],
+                      "hbm_bytes_written_per_pair": {"fused": 64 * ((frames(wl)[0] + 3) // 4) * ((frames(wl)[1] + 3) // 4) * 2,
+                                                     "separate": int(64 * ((frames(wl)[0] + 1) // 2) * ((frames(wl)[1] + 1) // 2) * 2 * 1.25)},
+                      "note": "bit-identical outputs (tests/test_gpu_kernels.py::test_sim_stem_pool_is_maxpool_of_the_fused_stem); "
+                              "the e2e path uses the fused one"}
+            log(f"[bench] pooled: fused {pf['value']:.0f} vs separate {ps['value']:.0f} pairs/s ({time.perf_counter() - t_start:.0f} s)")
+        except Exception as exc:
+            pooled = {"value": None, "error": repr(exc)}
     e2e = e2e_parity = parity = None
     if "e2e" in only and not args.no_e2e:
         e2e, e2e_parity, parity = e2e_records(ctx, wl, model, data, args)
@@ -1059,7 +1088,7 @@ def run_b200_arm(args, wl_name):
             },
             "roofline": main["roofline"], "cpu_baseline": cpu, "e2e": e2e, "e2e_parity": e2e_parity, "parity": parity,
             "gpu_launches": main["gpu_launches"], "clocks": main.get("clocks"), "phases_ms": main["phases_ms"],
-            "projection": main["projection"], "stem_out_GBps": main["stem_out_GBps"], "value_ragged": ragged,
+            "projection": main["projection"], "stem_out_GBps": main["stem_out_GBps"], "value_ragged": ragged, "value_pooled": pooled,
             "configs": configs, "strong": strong, "wall_s": time.perf_counter() - t_start,
         })
         emit(line)
@@ -1074,7 +1103,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg2")
-    ap.add_argument("--only", default="", help="comma list of records: main,ragged,e2e,configs,strong,cpu (default: all)")
+    ap.add_argument("--only", default="", help="comma list of records: main,ragged,pool,e2e,configs,strong,cpu (default: all)")
     ap.add_argument("--keywords", type=int, default=0, help="override K (keywords per GPU)")
     ap.add_argument("--utts", type=int, default=0, help="override U (utterances)")
     ap.add_argument("--max-pairs", type=int, default=1184, help="pairs per similarity+stem launch (8 x 148)")

@@ -13,13 +13,13 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 # KWS_B200_LIB: explicit path of another flavour of the same ABI (the -DKWS_DEBUG_HOOKS development build)
 LIB_PATH = os.environ.get("KWS_B200_LIB") or os.path.join(HERE, "libkws_b200.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 # constants of include/kws_b200.h
 F16, BF16 = 0, 1
 MLP_OUT_NORM_F16, MLP_OUT_RAW_F32, MLP_OUT_RAW_16 = 0, 1, 2
 PAIRS_ALL, PAIRS_DIAG, PAIRS_PER_KEYWORD = 0, 1, 2
-STEM_OUT_NCHW_F32, STEM_OUT_NHWC_BF16 = 0, 1
+STEM_OUT_NCHW_F32, STEM_OUT_NHWC_BF16, STEM_OUT_POOL_NHWC_BF16 = 0, 1, 2
 
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 
@@ -47,6 +47,8 @@ SIGNATURES = {
     "kws_sim_stem_supported": (_i, [_i, _i, _i, _i]),
     "kws_sim_stem_range": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "kws_sim_stem_ragged": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "kws_sim_stem_pool": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "kws_sim_stem_pool_workspace_bytes": (_sz, [_i, C.c_longlong, _i, _i]),
     "kws_resize_bilinear": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "kws_interp_rows": (_i, [_vp, _i, _i, _i, _i, C.POINTER(C.c_int32), _i, _i, _f, _vp, _vp]),
     "kws_sim_operand": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),

@@ -86,6 +86,10 @@ namespace kws {
 constexpr int G_THREADS = 384;
 constexpr int G_OC = 64;
 constexpr int G_TILE_OJ = 60;                      // output columns per item (2*59 + 6 = 124 <= 127 input px); slots 60..63 idle
+// POOL instances (MaxPool2d(3,2,1) behind the stem fused in, HF modeling_resnet.py:67,76-77): an item is 29 pooled columns =
+// stem columns [58 ct - 1, 58 ct + 57] (59 slots, slot 0 = the left neighbour the first pooling window needs)
+constexpr int G_POOL_OJ = 29;
+constexpr int G_TILE_OJ_POOL = 2 * G_POOL_OJ;
 constexpr int G_NR = 8;                            // ring slots per block = 4 quanta of 2 slots
 constexpr int G_BLOCK = (G_NR + 1) * 1024 + 64;    // 9280: +mirror slot, +64 keeps plane 1 on other banks
 constexpr int G_RING_BYTES = 8 * G_BLOCK;          // [k8 2][rp 2][plane 2]
@@ -105,7 +109,7 @@ constexpr int G_TMEM_SIM = 2 * G_ACC_COLS;         // similarity region starts a
 constexpr int G_TMEM_BIAS = 448;                   // 64 columns: the folded-BN bias, replicated in every lane
 constexpr int G_OUT_STAGE = 4 * 32 * 128;          // per epilogue warp: 32 pixels x 64 bf16 (SW128), source of its TMA stores
 constexpr int G_NPAIR = G_MAX_C / 2;                 // similarity tiles are handed over per pair of layers
-constexpr int G_NBAR = 2 * G_NS + 2 * G_NPAIR + 4 + 4 + 2 + 2 + 8;
+constexpr int G_NBAR = 2 * G_NS + 2 * G_NPAIR + 4 + 4 + 2 + 2 + 8 + 2;
 
 struct FusedParams {
   const uint4* w;     // fused stem weights (kws_pack_stem_fused)
@@ -131,6 +135,8 @@ struct FusedParams {
   const int32_t* kwd_len;  // optional [K]: valid frames of every keyword (rows >= len are zero in kwd_n); output rows whose
                            // receptive field lies beyond are relu(bias): no similarity, no stem MMAs, constant fill
   long long num_items;
+  void* pool_out;  // POOL instances: bf16 channels-last [pairs, Hp, Wp, 64] (max-pooled stem activation)
+  int Hp, Wp;      // pooled image: ceil(Ho / 2) x ceil(Wo / 2)
   int whatif;    // development what-if switches (KWS_DEBUG_HOOKS builds only; results are WRONG when set): 1 epilogue
                  // releases the accumulator at once and does nothing else | 2 no half-b shift (no mailbox, no shuffles) |
                  // 4 no TMA store | 8 stem issues kernel row 0 only | 16 similarity issues one of four k-steps
@@ -255,7 +261,11 @@ __device__ __forceinline__ ItemShape item_shape(const FusedParams& p, int L) {
 // compile-time constants -- the issuer loops are sensitive to every instruction (a run-time stage count cost 10 %).
 // RAGGED: keyword length table honoured (p.kwd_len); the dense instances carry none of its bookkeeping -- the role loops
 // are sensitive to every live register and instruction.
-template <bool NHWC, int ROWS, bool MULTI, int NHM = 2, bool S12 = false, bool RAGGED = false>
+// POOL: the 3x3 / stride-2 / pad-1 max-pool that follows the stem (HF ResNetEmbeddings.pooler) is applied before the
+// activation leaves the SM: the epilogue warps stage the bf16 tile as before, the otherwise idle warp 3 reduces it
+// (3 columns x 2 rows from the staging tile + the previous step's second row, carried in registers) and writes one
+// pooled row per step: 1.8 instead of 7.2 MB per pair, no separate max-pool pass.
+template <bool NHWC, int ROWS, bool MULTI, int NHM = 2, bool S12 = false, bool RAGGED = false, bool POOL = false>
 __global__ void __launch_bounds__(G_THREADS, 1)
 kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_constant__ CUtensorMap map_kwd,
                  const __grid_constant__ CUtensorMap map_out_lo, const __grid_constant__ CUtensorMap map_out_hi,
@@ -270,6 +280,10 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
   constexpr int NPAIR = 96 / ROWS;                // layer pairs the converters can hold: 6 / 3 / 2
   constexpr int QPC = ROWS / 4;                   // quanta per similarity chunk
   constexpr int NS = G_NS;                        // operand stages
+  static_assert(!POOL || NHWC, "the fused max-pool exists for the bf16 channels-last output only");
+  constexpr int TILE = POOL ? G_TILE_OJ_POOL : G_TILE_OJ;  // stem columns an item advances by
+  constexpr int COL_OFF = POOL ? 1 : 0;                    // slot s holds stem column TILE * ct + s - COL_OFF
+  constexpr int SLOTS = POOL ? G_TILE_OJ_POOL + 1 : G_TILE_OJ;  // pixel slots of a row that carry output
   uint8_t* s_ops = base;                          // NS * G_STAGE (each 1024-aligned)
   uint8_t* s_w = s_ops + NS * G_STAGE;            // p.w_bytes (multiple of 4096)
   uint8_t* s_ostage = s_w + kWbytes;              // G_OUT_STAGE (4 x 4 KB, each 1024-aligned); two sets when MULTI
@@ -284,6 +298,8 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
   uint64_t* afull = qempty + 4;           // [2] MMA commit -> epilogue (stem accumulator ready)
   uint64_t* aempty = afull + 2;           // [2] epilogue -> MMA
   uint64_t* pload = aempty + 2;           // [4][2] TMA load of the previous pass's partial sums -> epilogue warp, per staging set
+  uint64_t* pfull = pload + 8;            // POOL: epilogue warps -> pool warp (staging tile of a step written)
+  uint64_t* pempty = pfull + 1;           // POOL: pool warp -> epilogue warps (staging tile read)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + G_NBAR);
 
   const int warp = threadIdx.x >> 5;
@@ -328,6 +344,8 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
       mbar_init(&pload[2 * s], 1);
       mbar_init(&pload[2 * s + 1], 1);
     }
+    mbar_init(pfull, 128);
+    mbar_init(pempty, 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -356,7 +374,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
         const ItemShape sh = item_shape<RAGGED>(p, L_next);
         L_next = item_len<RAGGED>(p, it + gridDim.x);
         const int n_chunks = (sh.nQ + QPC - 1) / QPC;
-        const int jbase = 2 * G_TILE_OJ * w.ct - 3;  // input column of pixel x = 0 (OOB columns read as zero)
+        const int jbase = 2 * (TILE * w.ct - COL_OFF) - 3;  // input column of pixel x = 0 (OOB columns read as zero)
         for (int n = 0; n < n_chunks; ++n) {
           if (ROWS * n - 3 >= sh.L) continue;  // chunk entirely below the image / the keyword (zero rows): nothing to load
           for (int c = 0; c < kC; ++c) {
@@ -557,10 +575,10 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
           "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
           "%6}], [%2];" ::"r"(smem_u32(stage0 + set * G_OUT_STAGE)),
           "l"(reinterpret_cast<uint64_t>(my_map)), "r"(smem_u32(&pload[2 * q + set])), "r"(0),
-          "r"(ct * G_TILE_OJ + (q & 1) * 32), "r"(oi), "r"(pair)
+          "r"(ct * TILE + (q & 1) * 32 - COL_OFF), "r"(oi), "r"(pair)
           : "memory");
     };
-    auto tile_ok_at = [&](int ct, int oi) { return oi < p.Ho && ct * G_TILE_OJ + (q & 1) * 32 < p.Wo; };
+    auto tile_ok_at = [&](int ct, int oi) { return oi < p.Ho && ct * TILE + (q & 1) * 32 - COL_OFF < p.Wo; };
     if (MULTI && nhwc && p.prefetch == 1 && loads_prev && lane == 0 && (long long)blockIdx.x < p.num_items) {
       const ItemCoord w0 = decode_item(p, blockIdx.x);
       if (tile_ok_at(w0.ct, row_sel)) load_prev(0u, w0.ct, row_sel, (int)w0.pair);
@@ -573,8 +591,8 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
       const ItemCoord w = decode_item(p, it);
       const ItemShape sh = item_shape<RAGGED>(p, L_next);
       L_next = item_len<RAGGED>(p, it + gridDim.x);
-      const int oj = w.ct * G_TILE_OJ + ojl;
-      const bool col_ok = ojl < G_TILE_OJ && oj < p.Wo;
+      const int oj = w.ct * TILE + ojl - COL_OFF;
+      const bool col_ok = ojl < SLOTS && oj >= 0 && oj < p.Wo;
       for (int P = 0; P < sh.nP; ++P, ++acc_seq) {
         stage_const = false;
         const uint32_t acc = acc_seq & 1;
@@ -615,6 +633,10 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
             tmem_ld16(tmem_base + G_TMEM_BIAS + ((uint32_t)(q * 32) << 16) + grp * (16 * NH) + h * 16, vbias[h]);
           }
           if (grp == 0) {
+            // POOL: the pool warp must have read the previous step's tile out of the staging buffers before they are
+            // written again: here when the partial sums of a previous pass are TMA-loaded into them, else as late as
+            // possible (just before this step's first store, below)
+            if constexpr (POOL && MULTI) mbar_wait(pempty, (acc_seq & 1) ^ 1, 970);
             // the previous step's TMA store must have read this warp's staging buffer before it is reused
             if (lane == 0) {
               asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -630,7 +652,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
                   if (have && tile_ok_at(nct, noi))
                     asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(
                                      reinterpret_cast<uint64_t>(my_map)),
-                                 "r"(0), "r"(nct * G_TILE_OJ + (q & 1) * 32), "r"(noi), "r"(npair)
+                                 "r"(0), "r"(nct * TILE + (q & 1) * 32 - COL_OFF), "r"(noi), "r"(npair)
                                  : "memory");
                 }
               } else if (nhwc && MULTI && loads_prev) {
@@ -722,7 +744,14 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
               }
               // 16-byte chunks 2ch, 2ch+1 of this pixel's 128-byte row, 128B swizzle (chunk ^ (row & 7));
               // rows 28..31 of the hi warp are idle pixel slots and hold the mailboxes: never written here
-              if (lo_warp || lane < G_TILE_OJ - 32) {
+              if constexpr (POOL && !MULTI) {
+                if (grp == 0 && h == 0) mbar_wait(pempty, (acc_seq & 1) ^ 1, 970);
+              }
+              if (lo_warp || lane < SLOTS - 32) {
+                if (POOL && !ok) {  // outside the image: 0 never wins a max over post-ReLU values
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) o[e] = 0u;
+                }
                 *reinterpret_cast<uint4*>(c0p) = make_uint4(o[0], o[1], o[2], o[3]);
                 *reinterpret_cast<uint4*>(c1p) = make_uint4(o[4], o[5], o[6], o[7]);
               }
@@ -749,6 +778,9 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
         }
         if constexpr (nhwc) {
           if (MULTI && loads_prev && tile_ok) ++pl_seq[set];
+          if constexpr (POOL) {
+            mbar_arrive(pfull);  // this thread's part of the tile is in the staging buffer: over to the pool warp
+          } else {
           fence_proxy_async();
           __syncwarp();
           if (lane == 0 && tile_ok && !KWS_WHATIF(4)) {
@@ -768,6 +800,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
+          }
         }
         te_rest += KWS_CLK() - e1;
         if (warp == 4 && lane == 0) KWS_TRACE(1, acc_seq, 2);
@@ -776,7 +809,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
       // ---- fill steps (ragged keywords): output rows beyond the keyword are exactly relu(bias) --------------------
       // Only the pass that writes final values fills (single pass / last channel-group pass); the partial sums of the
       // earlier passes are never read for these rows.
-      if (RAGGED && sh.nP < p.nP && (!MULTI || p.acc_mode == 0 || p.acc_mode == 3)) {
+      if (RAGGED && !POOL && sh.nP < p.nP && (!MULTI || p.acc_mode == 0 || p.acc_mode == 3)) {
         const uint32_t t_bias = tmem_base + G_TMEM_BIAS + ((uint32_t)(q * 32) << 16);
         if constexpr (nhwc) {
           if (!stage_const) {
@@ -838,6 +871,86 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
       long long* o = p.dbg + (size_t)blockIdx.x * 32;
       o[5] = te_wait, o[6] = te_ld, o[7] = te_rest, o[12] = te_pl, o[13] = te_lds;
       for (int i = 0; i < 7; ++i) o[16 + i] = tp[i];
+    }
+  } else if (POOL && warp == 3) {
+    // ===================== pool warp: MaxPool2d(3, 2, 1) on the staged bf16 tile =====================
+    // Step P stages stem rows 2P and 2P+1 (slot s = stem column TILE ct + s - 1, zeros outside the image); pooled row P =
+    // max over rows 2P-1 .. 2P+1 and, for pooled column c of the item, slots 2c .. 2c+2.  Row 2P-1 is the previous
+    // step's second row: its column maxima are carried in registers.  Lane = (16-byte channel chunk j, pixel group g):
+    // pooled columns g, g+4, ..., 8 units per lane; one warp-wide LDS.128 reads four whole 128-byte pixel rows.
+    const int j = lane & 7, g4 = lane >> 3;
+    uint32_t rb[4];  // relu(bias) of this lane's 8 channels, bf16x2 (the constant rows of ragged keywords)
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      rb[e] = relu_bf16x2(pack_b64(__float_as_uint(__ldg(p.bias + 8 * j + 2 * e)), __float_as_uint(__ldg(p.bias + 8 * j + 2 * e + 1))));
+    auto bmax = [](uint32_t a, uint32_t b) {
+      uint32_t r;
+      asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+      return r;
+    };
+    // 16-byte chunk j of slot sl = 2 (g4 + 4 i) + t of staged row r: the four 32-pixel staging tiles are contiguous
+    // ([row r][half]), so the byte offset is r * 8192 + sl * 128 + swizzle, and the 128B swizzle (chunk ^ (slot & 7))
+    // does not depend on i: three base addresses + compile-time offsets
+    const uint8_t* pbase[3];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) pbase[t] = s_ostage + (2 * g4 + t) * 128 + ((j ^ ((2 * g4 + t) & 7)) << 4);
+    auto px = [&](int r, int i, int t) { return *reinterpret_cast<const uint4*>(pbase[t] + r * (2 * 32 * 128) + i * (8 * 128)); };
+    __nv_bfloat16* const pout = reinterpret_cast<__nv_bfloat16*>(p.pool_out);
+    uint32_t seq = 0;
+    int L_next = item_len<RAGGED>(p, blockIdx.x);
+    for (long long it = blockIdx.x; it < p.num_items; it += gridDim.x) {
+      const ItemCoord w = decode_item(p, it);
+      const ItemShape sh = item_shape<RAGGED>(p, L_next);
+      L_next = item_len<RAGGED>(p, it + gridDim.x);
+      uint4 carry[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) carry[i] = make_uint4(0u, 0u, 0u, 0u);
+      __nv_bfloat16* const obase = pout + ((size_t)w.pair * p.Hp * p.Wp + (size_t)w.ct * G_POOL_OJ + g4) * G_OC + 8 * j;
+      const int cols = p.Wp - w.ct * G_POOL_OJ;  // pooled columns of this item that exist
+      for (int P = 0; P < sh.nP; ++P, ++seq) {
+        mbar_wait(pfull, seq & 1, 980);
+        uint4 o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = g4 + 4 * i;
+          if (c < G_POOL_OJ) {
+            const uint4 a0 = px(0, i, 0), a1 = px(0, i, 1), a2 = px(0, i, 2);
+            const uint4 b0 = px(1, i, 0), b1 = px(1, i, 1), b2 = px(1, i, 2);
+            uint4 h1;
+            h1.x = bmax(bmax(b0.x, b1.x), b2.x), h1.y = bmax(bmax(b0.y, b1.y), b2.y);
+            h1.z = bmax(bmax(b0.z, b1.z), b2.z), h1.w = bmax(bmax(b0.w, b1.w), b2.w);
+            o[i].x = bmax(bmax(bmax(a0.x, a1.x), a2.x), bmax(h1.x, carry[i].x));
+            o[i].y = bmax(bmax(bmax(a0.y, a1.y), a2.y), bmax(h1.y, carry[i].y));
+            o[i].z = bmax(bmax(bmax(a0.z, a1.z), a2.z), bmax(h1.z, carry[i].z));
+            o[i].w = bmax(bmax(bmax(a0.w, a1.w), a2.w), bmax(h1.w, carry[i].w));
+            carry[i] = h1;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pempty);  // the staging tile may be overwritten
+        __nv_bfloat16* orow = obase + (size_t)P * p.Wp * G_OC;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = g4 + 4 * i;
+          if (c < G_POOL_OJ && c < cols) *reinterpret_cast<uint4*>(orow + i * (4 * G_OC)) = o[i];
+        }
+      }
+      // ragged keywords: stem rows >= 2 nP are exactly relu(bias) (zero similarity rows), so pooled row nP is the maximum
+      // of the carried row and that constant, and the rows below it are the constant
+      if (RAGGED && sh.nP < p.nP && (!MULTI || p.acc_mode == 0 || p.acc_mode == 3)) {
+        for (int P = sh.nP; P < p.nP; ++P) {
+          __nv_bfloat16* orow = obase + (size_t)P * p.Wp * G_OC;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int c = g4 + 4 * i;
+            if (c < G_POOL_OJ && c < cols) {
+              uint4 v = make_uint4(rb[0], rb[1], rb[2], rb[3]);
+              if (P == sh.nP) v = make_uint4(bmax(v.x, carry[i].x), bmax(v.y, carry[i].y), bmax(v.z, carry[i].z), bmax(v.w, carry[i].w));
+              *reinterpret_cast<uint4*>(orow + i * (4 * G_OC)) = v;
+            }
+          }
+        }
+      }
     }
   } else if (warp >= 8) {
     // ===================== converters: TMEM similarity rows -> fp16 ring =====================
@@ -1134,10 +1247,39 @@ extern "C" int kws_sim_stem_range(const void* kwd_n, const void* utt_n, int C, i
                              out_mode, out, stream);
 }
 
+static int sim_stem_core(const void* kwd_n, const void* utt_n, const int32_t* kwd_len, int C, int K, int U, int Tk, int Tu,
+                         int Dk, int pair_mode, int k0, int nk, int u0, int nu, const void* w_fused, const float* bias,
+                         int out_mode, void* out, void* workspace, void* stream);
+
 extern "C" int kws_sim_stem_ragged(const void* kwd_n, const void* utt_n, const int32_t* kwd_len, int C, int K, int U,
                                    int Tk, int Tu, int Dk, int pair_mode, int k0, int nk, int u0, int nu,
                                    const void* w_fused, const float* bias, int out_mode, void* out, void* stream) {
+  KWS_CHECK_ARG(out_mode != KWS_STEM_OUT_POOL_NHWC_BF16, "sim_stem: the pooled output is kws_sim_stem_pool's");
+  return sim_stem_core(kwd_n, utt_n, kwd_len, C, K, U, Tk, Tu, Dk, pair_mode, k0, nk, u0, nu, w_fused, bias, out_mode, out,
+                       nullptr, stream);
+}
+
+// Bytes of the partial-sum workspace kws_sim_stem_pool needs for `pairs` pairs per call: 0 up to 12 layers (single pass).
+extern "C" size_t kws_sim_stem_pool_workspace_bytes(int C, long long pairs, int Tk, int Tu) {
+  if (C <= G_MAX_C || pairs <= 0 || Tk <= 0 || Tu <= 0) return 0;
+  return (size_t)pairs * ((Tk + 1) / 2) * ((Tu + 1) / 2) * G_OC * 2;
+}
+
+extern "C" int kws_sim_stem_pool(const void* kwd_n, const void* utt_n, const int32_t* kwd_len, int C, int K, int U, int Tk,
+                                 int Tu, int Dk, int pair_mode, int k0, int nk, int u0, int nu, const void* w_fused,
+                                 const float* bias, void* out, void* workspace, void* stream) {
+  return sim_stem_core(kwd_n, utt_n, kwd_len, C, K, U, Tk, Tu, Dk, pair_mode, k0, nk, u0, nu, w_fused, bias,
+                       KWS_STEM_OUT_POOL_NHWC_BF16, out, workspace, stream);
+}
+
+static int sim_stem_core(const void* kwd_n, const void* utt_n, const int32_t* kwd_len, int C, int K, int U, int Tk, int Tu,
+                         int Dk, int pair_mode, int k0, int nk, int u0, int nu, const void* w_fused, const float* bias,
+                         int out_mode, void* out, void* workspace, void* stream) {
   KWS_CHECK_ARG(kwd_n && utt_n && w_fused && bias && out, "sim_stem: null pointer");
+  const bool pool = out_mode == KWS_STEM_OUT_POOL_NHWC_BF16;
+  KWS_CHECK_ARG(!pool || C <= G_MAX_C || workspace, "sim_stem_pool: C=%d > %d layers needs the partial-sum workspace", C, G_MAX_C);
+  KWS_CHECK_ARG(!pool || g_multi_prefetch != 1, "sim_stem_pool: needs partial-sum prefetch mode 0 or 2");
+  KWS_CHECK_ARG(!pool || (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "sim_stem_pool: workspace must be 16-byte aligned");
   KWS_CHECK_ARG(kwd_len == nullptr || pair_mode != KWS_PAIRS_PER_KEYWORD,
                 "sim_stem: a keyword length table cannot be combined with KWS_PAIRS_PER_KEYWORD");
   KWS_CHECK_ARG(kwd_len == nullptr || g_multi_prefetch != 1, "sim_stem: ragged keywords need prefetch mode 0 or 2");
@@ -1145,7 +1287,7 @@ extern "C" int kws_sim_stem_ragged(const void* kwd_n, const void* utt_n, const i
   KWS_CHECK_ARG(k0 >= 0 && nk > 0 && k0 + nk <= K, "sim_stem: keyword range [%d,%d) outside [0,%d)", k0, k0 + nk, K);
   KWS_CHECK_ARG(u0 >= 0 && nu > 0 && u0 + nu <= U, "sim_stem: utterance range [%d,%d) outside [0,%d)", u0, u0 + nu, U);
   KWS_CHECK_ARG(C <= G_MAX_C_TOTAL, "sim_stem: C=%d > %d layers", C, G_MAX_C_TOTAL);
-  KWS_CHECK_ARG(C <= G_MAX_C || out_mode == KWS_STEM_OUT_NHWC_BF16,
+  KWS_CHECK_ARG(C <= G_MAX_C || out_mode == KWS_STEM_OUT_NHWC_BF16 || pool,
                 "sim_stem: C=%d > %d layers needs the bf16 channels-last output (multi-pass partial sums)", C, G_MAX_C);
   KWS_CHECK_ARG(Dk % 64 == 0 && Dk >= 64, "sim_stem: Dk=%d must be a multiple of 64", Dk);
   KWS_CHECK_ARG(pair_mode == KWS_PAIRS_ALL || pair_mode == KWS_PAIRS_DIAG || pair_mode == KWS_PAIRS_PER_KEYWORD,
@@ -1154,7 +1296,7 @@ extern "C" int kws_sim_stem_ragged(const void* kwd_n, const void* utt_n, const i
                 "sim_stem: KWS_PAIRS_DIAG needs U == K and equal ranges (got K=%d U=%d)", K, U);
   KWS_CHECK_ARG(pair_mode != KWS_PAIRS_PER_KEYWORD || (long long)K * U < (1ll << 31) / (C > 0 ? C : 1),
                 "sim_stem: KWS_PAIRS_PER_KEYWORD bank of K*U=%lld items too large", (long long)K * U);
-  KWS_CHECK_ARG(out_mode == KWS_STEM_OUT_NCHW_F32 || out_mode == KWS_STEM_OUT_NHWC_BF16, "sim_stem: bad out_mode %d",
+  KWS_CHECK_ARG(out_mode == KWS_STEM_OUT_NCHW_F32 || out_mode == KWS_STEM_OUT_NHWC_BF16 || pool, "sim_stem: bad out_mode %d",
                 out_mode);
   KWS_CHECK_ARG((reinterpret_cast<uintptr_t>(w_fused) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                 "sim_stem: pointers must be 16-byte aligned");
@@ -1176,19 +1318,21 @@ extern "C" int kws_sim_stem_ragged(const void* kwd_n, const void* utt_n, const i
   {
     // bf16 channels-last activation [pairs, Ho, Wo, 64]; one box = 32 (lo warp) or 28 (hi warp: slots 32..59)
     // pixels x 64 channels of one output row.  (Encoded for the fp32 NCHW mode as well, where it is not used.)
+    // POOL: the full-resolution tiles only exist as the partial sums of a multi-pass job, in the workspace
+    void* full = pool ? (workspace ? workspace : out) : out;  // (single-pass POOL: maps encoded but never used)
     const uint64_t dims[4] = {64, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)n_pairs};
     const uint64_t strides[3] = {128, 128ull * Wo, 128ull * Wo * Ho};
     const uint32_t box_lo[4] = {64, 32, 1, 1}, box_hi[4] = {64, G_TILE_OJ - 32, 1, 1};
-    if (int e = make_tensor_map(&mo_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, dims, strides, box_lo,
+    if (int e = make_tensor_map(&mo_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, full, dims, strides, box_lo,
                                 CU_TENSOR_MAP_SWIZZLE_128B))
       return e;
-    if (int e = make_tensor_map(&mo_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, dims, strides, box_hi,
+    if (int e = make_tensor_map(&mo_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, full, dims, strides, box_hi,
                                 CU_TENSOR_MAP_SWIZZLE_128B))
       return e;
-    if (int e = make_tensor_map(&mo_lo_f16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, out, dims, strides, box_lo,
+    if (int e = make_tensor_map(&mo_lo_f16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, full, dims, strides, box_lo,
                                 CU_TENSOR_MAP_SWIZZLE_128B))
       return e;
-    if (int e = make_tensor_map(&mo_hi_f16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, out, dims, strides, box_hi,
+    if (int e = make_tensor_map(&mo_hi_f16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, full, dims, strides, box_hi,
                                 CU_TENSOR_MAP_SWIZZLE_128B))
       return e;
   }
@@ -1205,13 +1349,12 @@ extern "C" int kws_sim_stem_ragged(const void* kwd_n, const void* utt_n, const i
   p.col_tiles = (p.Wo + G_TILE_OJ - 1) / G_TILE_OJ;
   p.nP = (p.Ho + 1) / 2;
   p.nQ = p.nP + 2;
+  p.Hp = (Ho + 1) / 2, p.Wp = (Wo + 1) / 2;
+  p.pool_out = pool ? out : nullptr;
+  const int col_tiles_full = p.col_tiles, col_tiles_pool = (p.Wp + G_POOL_OJ - 1) / G_POOL_OJ;
 
   p.diag = pair_mode == KWS_PAIRS_DIAG;
-  p.num_items = (long long)nk * (p.diag ? 1 : nu) * p.col_tiles;
-  long long grid = p.num_items;
   const int sms = sm_count();
-  if (grid > sms) grid = sms;
-  if (g_fused_grid_limit > 0 && grid > g_fused_grid_limit) grid = g_fused_grid_limit;
   p.dbg = g_fused_dbg;
   p.whatif = g_fused_whatif;
   p.kwd_len = kwd_len;
@@ -1225,6 +1368,13 @@ extern "C" int kws_sim_stem_ragged(const void* kwd_n, const void* utt_n, const i
     p.n_mma = fused_n_mma(Cg);
     p.acc_mode = n_groups == 1 ? 0 : (g == 0 ? 1 : (g == n_groups - 1 ? 3 : 2));
     p.w_bytes = (int)fused_group_bytes(Cg);
+    // the pass that writes final values pools (29 pooled columns per item); earlier passes write full-resolution partial sums
+    const bool pool_pass = pool && (p.acc_mode == 0 || p.acc_mode == 3);
+    p.col_tiles = pool_pass ? col_tiles_pool : col_tiles_full;
+    p.num_items = (long long)nk * (p.diag ? 1 : nu) * p.col_tiles;
+    long long grid = p.num_items;
+    if (grid > sms) grid = sms;
+    if (g_fused_grid_limit > 0 && grid > g_fused_grid_limit) grid = g_fused_grid_limit;
     const int rows = n_groups > 1 ? 16 : (g_fused_rows > 0 ? g_fused_rows : (Cg <= 4 ? 48 : (Cg <= 6 ? 32 : 16)));
     KWS_CHECK_ARG(rows == 16 || (rows == 32 && Cg <= 6) || (rows == 48 && Cg <= 4), "sim_stem: bad chunk rows %d", rows);
     p.n_chunks = (p.nQ + rows / 4 - 1) / (rows / 4);
@@ -1237,7 +1387,7 @@ extern "C" int kws_sim_stem_ragged(const void* kwd_n, const void* utt_n, const i
                                   CU_TENSOR_MAP_SWIZZLE_128B))
         return e;
     }
-    const bool nh = out_mode == KWS_STEM_OUT_NHWC_BF16;
+    const bool nh = out_mode == KWS_STEM_OUT_NHWC_BF16 || pool;
     void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, FusedParams);
     const bool s12 = Cg == 12 && p.nkb == 1 && g_fused_s12;
     const bool ragged = kwd_len != nullptr;
@@ -1263,6 +1413,22 @@ extern "C" int kws_sim_stem_ragged(const void* kwd_n, const void* utt_n, const i
              : rows == 32 ? (nh ? kws_fused_kernel<true, 32, false> : kws_fused_kernel<false, 32, false>)
                           : (nh ? kws_fused_kernel<true, 16, false> : kws_fused_kernel<false, 16, false>);
       if (rows == 16 && nh && s12) kern = kws_fused_kernel<true, 16, false, 2, true>;
+    }
+    if (pool_pass) {
+      if (p.acc_mode == 3) {
+        if (ragged)
+          kern = s12 ? kws_fused_kernel<true, 16, true, 2, true, true, true> : kws_fused_kernel<true, 16, true, 2, false, true, true>;
+        else
+          kern = s12 ? kws_fused_kernel<true, 16, true, 2, true, false, true> : kws_fused_kernel<true, 16, true, 2, false, false, true>;
+      } else if (ragged) {
+        kern = rows == 48 ? kws_fused_kernel<true, 48, false, 2, false, true, true>
+               : rows == 32 ? kws_fused_kernel<true, 32, false, 2, false, true, true>
+               : s12 ? kws_fused_kernel<true, 16, false, 2, true, true, true> : kws_fused_kernel<true, 16, false, 2, false, true, true>;
+      } else {
+        kern = rows == 48 ? kws_fused_kernel<true, 48, false, 2, false, false, true>
+               : rows == 32 ? kws_fused_kernel<true, 32, false, 2, false, false, true>
+               : s12 ? kws_fused_kernel<true, 16, false, 2, true, false, true> : kws_fused_kernel<true, 16, false, 2, false, false, true>;
+      }
     }
     const size_t smem = g_smem_bytes(rows, p.n_mma, p.acc_mode != 0 && p.prefetch == 1);
     KWS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

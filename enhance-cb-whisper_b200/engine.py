@@ -177,13 +177,20 @@ class KWSEngine:
         ``launch_events``: if a list, a (start, end) CUDA-event pair around every pair-kernel launch is
         appended (bench.py reads per-launch durations from them).  ``kwd_len``: int32 [K] valid frames of every
         keyword at the similarity's resolution (``keyword_lengths``): the fused kernel then skips the rows beyond a
-        keyword (bit-identical output); ignored by the un-fused path."""
+        keyword (bit-identical output); ignored by the un-fused path.
+        ``out_mode`` STEM_OUT_POOL_NHWC_BF16: ``consume`` receives the MAX-POOLED stem activation
+        ([pairs,64,ceil(Ho/2),ceil(Wo/2)] bf16 channels_last, what ResNetEmbeddings hands to the encoder) from the fused
+        similarity + stem + pool kernel; the stem activation itself never reaches HBM (un-fused shapes: kws_sim ->
+        kws_stem -> kws_maxpool_nhwc)."""
         Cc, K, Tk, Dk = kwd_n.shape
         _, U, Tu, _ = utt_n.shape
         bufs = bufs if bufs is not None else {}
         fused = self.fused(Tk, Tu, out_mode)
         Ho, Wo = (Tk + 1) // 2, (Tu + 1) // 2
         f32 = out_mode == ops.STEM_OUT_NCHW_F32
+        pool = out_mode == ops.STEM_OUT_POOL_NHWC_BF16
+        if pool and fused:
+            Ho, Wo = (Ho + 1) // 2, (Wo + 1) // 2  # the buffer holds the pooled activation
         n = 0
         for k0, k1, u0, u1 in self.pair_chunks(K, U, Tk, Tu, max_pairs):
             np_ = (k1 - k0) * (u1 - u0)
@@ -195,7 +202,13 @@ class KWSEngine:
             if launch_events is not None:
                 ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 ev[0].record()
-            if fused:
+            if fused and pool:
+                need = ops.sim_stem_pool_workspace_bytes(Cc, np_, Tk, Tu)
+                if need and ("pool_ws" not in bufs or bufs["pool_ws"].numel() < need):
+                    bufs["pool_ws"] = torch.empty(need, dtype=torch.uint8, device=kwd_n.device)
+                st = ops.sim_stem_pool(kwd_n, utt_n, self.w.stem_wf, self.w.stem_b, out=bufs[keyo], k_range=(k0, k1),
+                                       u_range=(u0, u1), kwd_len=kwd_len, workspace=bufs.get("pool_ws"))
+            elif fused:
                 st = ops.sim_stem(kwd_n, utt_n, self.w.stem_wf, self.w.stem_b, out_mode, out=bufs[keyo],
                                   k_range=(k0, k1), u_range=(u0, u1), kwd_len=kwd_len)
             else:
@@ -207,8 +220,10 @@ class KWSEngine:
                                               device=kwd_n.device)
                 _, f16 = ops.sim(kk, uu, want_f32=False, want_f16=True, out_f16=bufs[key16])
                 shape = (np_, 64, Ho, Wo) if f32 else (np_, Ho, Wo, 64)
-                st = ops.stem(f16, Tu, self.w.stem_w, self.w.stem_b, out_mode,
+                st = ops.stem(f16, Tu, self.w.stem_w, self.w.stem_b, ops.STEM_OUT_NHWC_BF16 if pool else out_mode,
                               out=bufs[keyo][: np_ * 64 * Ho * Wo].view(shape))
+                if pool:
+                    st = ops.maxpool_nhwc(st)
             if launch_events is not None:
                 ev[1].record()
                 launch_events.append(ev + (np_,))

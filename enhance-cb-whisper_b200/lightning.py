@@ -36,8 +36,11 @@ from .model import B200ForwardMixin
 
 class KWSModelB200(B200ForwardMixin, _ReferenceKWSModel):
     def __init__(self, *args, b200_body_dtype: str = "float32", b200_return_features: bool = True,
-                 b200_layer_idx=None, b200_mlp_dtype: str = "float16", **kwargs):
+                 b200_layer_idx=None, b200_mlp_dtype: str = "float16", b200_fused_pool: bool = True,
+                 b200_ragged: bool = True, **kwargs):
         super().__init__(*args, **kwargs)
+        self.b200_fused_pool = b200_fused_pool
+        self.b200_ragged = b200_ragged
         self.b200_body_dtype = b200_body_dtype
         self.b200_return_features = b200_return_features
         self.b200_layer_idx = b200_layer_idx

@@ -109,6 +109,7 @@ class B200ForwardMixin:
     b200_return_features: bool = True  # materialise KWSOutput.features (fp32) like the reference
     b200_layer_idx: Optional[Sequence[int]] = None  # explicit layer selection into the given stack
     b200_mlp_dtype: str = "float16"  # projector GEMM operands: "float16" (parity) | "bfloat16" (range-safe)
+    b200_fused_pool: bool = True  # "bfloat16" body: MaxPool2d(3,2,1) behind the stem inside the fused kernel (kws_sim_stem_pool)
     b200_ragged: bool = True  # batched scoring: carry the keyword lengths (from the frame masks) into the fused kernel,
     #                           which skips the rows beyond a keyword -- bit-identical output (kws_sim_stem_ragged)
 
@@ -157,7 +158,19 @@ class B200ForwardMixin:
             self._body_lowp = None
         return self._engine
 
-    def _body(self, stem_act: torch.Tensor) -> torch.Tensor:
+    def _b200_out_mode(self) -> int:
+        """What the similarity+stem kernels hand to the body: fp32 NCHW stem activation (parity body), bf16
+        channels_last stem activation, or -- fused body with ``b200_fused_pool`` -- the max-pooled activation."""
+        if self.b200_body_dtype == "float32":
+            return ops.STEM_OUT_NCHW_F32
+        if self.b200_body_dtype == "bfloat16" and self.b200_fused_pool:
+            return ops.STEM_OUT_POOL_NHWC_BF16
+        return ops.STEM_OUT_NHWC_BF16
+
+    def _body(self, stem_act: torch.Tensor, pooled: bool = False) -> torch.Tensor:
+        """Everything behind the stem (or, ``pooled``, behind the stem's max-pool) -> logits."""
+        if pooled and self.b200_body_dtype != "bfloat16":
+            raise ValueError("a pooled activation is only produced for b200_body_dtype='bfloat16'")
         if self.b200_body_dtype == "float32":
             return run_body(self.model, stem_act)
         kind = self.b200_body_dtype
@@ -174,7 +187,7 @@ class B200ForwardMixin:
             return run_body(self._body_lowp[1], stem_act)
         # "bfloat16": BatchNorms folded, one cuDNN fused conv+bias(+residual)+ReLU per convolution (body.py);
         # max-pool in libkws_b200 (HBM-bound kernel; torch's channels-last bf16 max_pool2d runs at ~0.7 TB/s)
-        return self._body_lowp[1](ops.maxpool_nhwc(stem_act), pooled=True)
+        return self._body_lowp[1](stem_act if pooled else ops.maxpool_nhwc(stem_act), pooled=True)
 
     # ---- the reference-facing call -------------------------------------------------
     def forward(self, kwd_features: torch.Tensor, utt_features: torch.Tensor, labels: torch.Tensor = None,
@@ -203,18 +216,24 @@ class B200ForwardMixin:
             kwd_n = eng.compress(kwd_features, kwd_mask, layer_idx)
             utt_n = self._b200_compress_utt(eng, utt_features, utt_mask, layer_idx)
             Tk_s, Tu_s = kwd_n.shape[2], utt_n.shape[2]
-            lowp = self.b200_body_dtype != "float32"
-            out_mode = ops.STEM_OUT_NHWC_BF16 if lowp else ops.STEM_OUT_NCHW_F32
+            out_mode = self._b200_out_mode()
+            pooled = False
             f32 = None
             if not self.b200_return_features and eng.fused(Tk_s, Tu_s, out_mode):
                 # KWSOutput.features is read by no caller of the reference; without it the
                 # similarity tensor never reaches HBM
-                st = ops.sim_stem(kwd_n, utt_n, eng.w.stem_wf, eng.w.stem_b, out_mode, diag=diag,
-                                  kwd_len=self._b200_kwd_len(kwd_mask))
+                if out_mode == ops.STEM_OUT_POOL_NHWC_BF16:
+                    st = ops.sim_stem_pool(kwd_n, utt_n, eng.w.stem_wf, eng.w.stem_b, diag=diag,
+                                           kwd_len=self._b200_kwd_len(kwd_mask))
+                    pooled = True
+                else:
+                    st = ops.sim_stem(kwd_n, utt_n, eng.w.stem_wf, eng.w.stem_b, out_mode, diag=diag,
+                                      kwd_len=self._b200_kwd_len(kwd_mask))
             else:
                 f32, f16 = ops.sim(kwd_n, utt_n, want_f32=self.b200_return_features, want_f16=True, diag=diag)
-                st = ops.stem(f16, Tu_s, eng.w.stem_w, eng.w.stem_b, out_mode)
-            logits = self._body(st).float()
+                st = ops.stem(f16, Tu_s, eng.w.stem_w, eng.w.stem_b,
+                              ops.STEM_OUT_NCHW_F32 if out_mode == ops.STEM_OUT_NCHW_F32 else ops.STEM_OUT_NHWC_BF16)
+            logits = self._body(st, pooled).float()
         features = None
         if f32 is not None:
             features = f32 if diag else f32[:, 0]
@@ -263,12 +282,13 @@ class B200ForwardMixin:
         kwd_n = eng.compress(kwd, kwd_mask, layer_idx)
         utt_n = eng.compress(utt, utt_mask, layer_idx)
         logits = torch.empty((kwd.shape[0], 1, 2), dtype=torch.float32, device=kwd.device)
-        lowp = self.b200_body_dtype != "float32"
+        out_mode = self._b200_out_mode()
+        pooled = out_mode == ops.STEM_OUT_POOL_NHWC_BF16
 
         def consume(k0, k1, u0, u1, st):
-            logits[k0:k1, u0:u1] = self._body(st).float().view(k1 - k0, u1 - u0, 2)
+            logits[k0:k1, u0:u1] = self._body(st, pooled).float().view(k1 - k0, u1 - u0, 2)
 
-        eng.hot_path(kwd_n, utt_n, ops.STEM_OUT_NHWC_BF16 if lowp else ops.STEM_OUT_NCHW_F32,
+        eng.hot_path(kwd_n, utt_n, out_mode,
                      int(getattr(self, "b200_step_pairs", 256)), consume, kwd_len=self._b200_kwd_len(kwd_mask))
         return logits[:, 0]
 
@@ -416,14 +436,14 @@ class B200ForwardMixin:
             kwd_len = KWSEngine.keyword_lengths(kwd_mask.to(dev, non_blocking=True))
         hot = hotword_mask.to(dev, non_blocking=True) if hotword_mask is not None else None
         logits = torch.empty((K, U, 2), dtype=torch.float32, device=dev)
-        lowp = self.b200_body_dtype != "float32"
-        out_mode = ops.STEM_OUT_NHWC_BF16 if lowp else ops.STEM_OUT_NCHW_F32
+        out_mode = self._b200_out_mode()
+        pooled = out_mode == ops.STEM_OUT_POOL_NHWC_BF16
         bufs = self._stage.setdefault("bufs", {}) if getattr(self, "_stage", None) is not None else {}
         for us, ms, u0, u1 in self._host_slabs("utt", utt_features, utt_mask, utt_slab, dev):
             utt_n = eng.compress(us, ms, layer_idx)
 
             def consume(a0, a1, b0, b1, st, u0=u0):
-                logits[a0:a1, u0 + b0:u0 + b1] = self._body(st).float().view(a1 - a0, b1 - b0, 2)
+                logits[a0:a1, u0 + b0:u0 + b1] = self._body(st, pooled).float().view(a1 - a0, b1 - b0, 2)
 
             eng.hot_path(kwd_n, utt_n, out_mode, max_pairs, consume, bufs=bufs, kwd_len=kwd_len)
         hw = None
@@ -439,13 +459,13 @@ class B200ForwardMixin:
         eng = self.prepare(kwd_n.device)
         K, U = kwd_n.shape[1], utt_n.shape[1]
         logits = torch.empty((K, U, 2), dtype=torch.float32, device=kwd_n.device)
-        lowp = self.b200_body_dtype != "float32"
+        out_mode = self._b200_out_mode()
+        pooled = out_mode == ops.STEM_OUT_POOL_NHWC_BF16
 
         def consume(k0, k1, u0, u1, st):
-            logits[k0:k1, u0:u1] = self._body(st).float().view(k1 - k0, u1 - u0, 2)
+            logits[k0:k1, u0:u1] = self._body(st, pooled).float().view(k1 - k0, u1 - u0, 2)
 
-        eng.hot_path(kwd_n, utt_n, ops.STEM_OUT_NHWC_BF16 if lowp else ops.STEM_OUT_NCHW_F32, max_pairs, consume,
-                     kwd_len=kwd_len if self.b200_ragged else None)
+        eng.hot_path(kwd_n, utt_n, out_mode, max_pairs, consume, kwd_len=kwd_len if self.b200_ragged else None)
         hw = None
         if hotword_mask is not None:
             hw = hotword_mask.to(logits.device, torch.float32).view(K, 1).expand(K, U).contiguous().view(-1)

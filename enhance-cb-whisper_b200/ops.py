@@ -14,7 +14,7 @@ import torch
 from . import _lib
 from ._lib import (BF16, F16, MLP_OUT_NORM_F16, MLP_OUT_RAW_16, MLP_OUT_RAW_F32, PAIRS_ALL, PAIRS_DIAG, PAIRS_PER_KEYWORD,
                    STEM_OUT_NCHW_F32,
-                   STEM_OUT_NHWC_BF16, KWSError)
+                   STEM_OUT_NHWC_BF16, STEM_OUT_POOL_NHWC_BF16, KWSError)
 
 TORCH16 = {F16: torch.float16, BF16: torch.bfloat16}
 
@@ -316,7 +316,7 @@ def stem(feat_f16: torch.Tensor, Tu: int, w_packed: torch.Tensor, bias: torch.Te
 def sim_stem_supported(Cc: int, Tk: int, Tu: int, Dk: int, out_mode: int = STEM_OUT_NHWC_BF16) -> bool:
     """kws_sim_stem_supported: 1 = both output modes, 2 = bf16 channels-last only (C > 12, multi-pass), 0 = no."""
     r = _lib.load().kws_sim_stem_supported(Cc, Tk, Tu, Dk)
-    return r == 1 or (r == 2 and out_mode == STEM_OUT_NHWC_BF16)
+    return r == 1 or (r == 2 and out_mode in (STEM_OUT_NHWC_BF16, STEM_OUT_POOL_NHWC_BF16))
 
 
 @_guard
@@ -366,6 +366,47 @@ def sim_stem(kwd_n: torch.Tensor, utt_n: torch.Tensor, w_fused: torch.Tensor, bi
     if out_mode == STEM_OUT_NHWC_BF16:
         return view.permute(0, 3, 1, 2)
     return view
+
+
+def sim_stem_pool_workspace_bytes(Cc: int, pairs: int, Tk: int, Tu: int) -> int:
+    """Bytes of partial-sum workspace sim_stem_pool needs for ``pairs`` pairs per call (0 up to 12 layers)."""
+    return int(_lib.load().kws_sim_stem_pool_workspace_bytes(int(Cc), int(pairs), int(Tk), int(Tu)))
+
+
+@_guard
+def sim_stem_pool(kwd_n: torch.Tensor, utt_n: torch.Tensor, w_fused: torch.Tensor, bias: torch.Tensor,
+                  diag: bool = False, out: Optional[torch.Tensor] = None, k_range: Optional[Tuple[int, int]] = None,
+                  u_range: Optional[Tuple[int, int]] = None, kwd_len: Optional[torch.Tensor] = None,
+                  workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Fused similarity + stem + MaxPool2d(3,2,1) (kws_sim_stem_pool): the activation ResNetEmbeddings hands to the
+    encoder, bf16 channels_last [N,64,ceil(Ho/2),ceil(Wo/2)]; arguments as sim_stem.  More than 12 layers need a
+    ``workspace`` for the partial sums of the channel-group passes (allocated here when not given)."""
+    lib = _lib.load()
+    Cc, K, Tk, Dk = kwd_n.shape
+    Cu, U, Tu, Dku = utt_n.shape
+    if Cc != Cu or Dk != Dku:
+        raise KWSError(f"operand mismatch: kwd {tuple(kwd_n.shape)} vs utt {tuple(utt_n.shape)}")
+    k0, k1 = k_range if k_range is not None else (0, K)
+    u0, u1 = u_range if u_range is not None else (0, U)
+    pairs = (k1 - k0) if diag else (k1 - k0) * (u1 - u0)
+    Ho, Wo = (Tk + 1) // 2, (Tu + 1) // 2
+    Hp, Wp = (Ho + 1) // 2, (Wo + 1) // 2
+    if out is None:
+        out = torch.empty((pairs, Hp, Wp, 64), dtype=torch.bfloat16, device=kwd_n.device)
+    elif out.dtype != torch.bfloat16 or out.numel() < pairs * 64 * Hp * Wp:
+        raise KWSError(f"out buffer too small / wrong dtype for {pairs} pooled pairs")
+    if kwd_len is not None and (kwd_len.dtype != torch.int32 or kwd_len.numel() != K):
+        raise KWSError(f"kwd_len must be int32 [K={K}]")
+    need = lib.kws_sim_stem_pool_workspace_bytes(Cc, pairs, Tk, Tu)
+    if need and (workspace is None or workspace.numel() * workspace.element_size() < need):
+        workspace = torch.empty(need, dtype=torch.uint8, device=kwd_n.device)
+    check(lib.kws_sim_stem_pool(_cuda(kwd_n, "kwd_n", torch.float16), _cuda(utt_n, "utt_n", torch.float16),
+                                _cuda(kwd_len, "kwd_len", torch.int32), Cc, K, U, Tk, Tu, Dk,
+                                PAIRS_DIAG if diag else PAIRS_ALL, k0, k1 - k0, u0, u1 - u0,
+                                _cuda(w_fused, "w_fused", torch.float16), _cuda(bias, "bias", torch.float32),
+                                _cuda(out, "out"), _cuda(workspace, "workspace") if need else None, _stream()),
+          "kws_sim_stem_pool", launches=(Cc + 11) // 12)
+    return out.view(-1)[: pairs * 64 * Hp * Wp].view(pairs, Hp, Wp, 64).permute(0, 3, 1, 2)
 
 
 @_guard

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define KWS_ABI_VERSION 7
+#define KWS_ABI_VERSION 8
 
 /* 16-bit operand formats (same encoding as the tcgen05 kind::f16 descriptor) */
 #define KWS_F16 0  /* IEEE half: 10-bit mantissa; for L2-normalised data and sane weights */
@@ -58,6 +58,7 @@ extern "C" {
 /* kws_stem out_mode */
 #define KWS_STEM_OUT_NCHW_F32 0  /* fp32 [pairs,64,Ho,Wo]   (parity with the reference) */
 #define KWS_STEM_OUT_NHWC_BF16 1 /* bf16 [pairs,Ho,Wo,64]   (channels_last hand-off)    */
+#define KWS_STEM_OUT_POOL_NHWC_BF16 2 /* bf16 [pairs,ceil(Ho/2),ceil(Wo/2),64]: stem + MaxPool2d(3,2,1), kws_sim_stem_pool only */
 
 int kws_abi_version(void);
 /* thread-local description of the last non-zero return value */
@@ -206,6 +207,19 @@ int kws_sim_stem_range(const void* kwd_n, const void* utt_n, int C, int K, int U
 int kws_sim_stem_ragged(const void* kwd_n, const void* utt_n, const int32_t* kwd_len, int C, int K, int U, int Tk, int Tu,
                         int Dk, int pair_mode, int k0, int nk, int u0, int nu, const void* w_fused, const float* bias,
                         int out_mode, void* out, void* stream);
+
+/* Similarity + stem + the max-pool that follows it, in one kernel: what ResNetEmbeddings hands to the
+ * encoder, `pooler(embedder(x))` = MaxPool2d(kernel 3, stride 2, padding 1) of relu(BN(conv7x7/2)) -- HF
+ * modeling_resnet.py:57-78 (embedder :67, pooler :76-77), reached through src/efficient_kws/resnet.py:53.
+ * out: bf16 channels-last [pairs, ceil(Ho/2), ceil(Wo/2), 64], 1.8 instead of 7.2 MB per pair at 150x1500; the stem
+ * activation itself never reaches HBM.  Bit-identical to kws_maxpool_nhwc applied to kws_sim_stem_ragged's bf16 output
+ * (the maximum commutes with the monotone bf16 rounding).  Arguments as kws_sim_stem_ragged (kwd_len may be NULL).
+ * More than 12 layers run as channel-group passes whose fp16 partial sums live in `workspace`
+ * (kws_sim_stem_pool_workspace_bytes(C, pairs of this call, Tk, Tu) bytes, 16-byte aligned; NULL for C <= 12). */
+size_t kws_sim_stem_pool_workspace_bytes(int C, long long pairs, int Tk, int Tu);
+int kws_sim_stem_pool(const void* kwd_n, const void* utt_n, const int32_t* kwd_len, int C, int K, int U, int Tk, int Tu,
+                      int Dk, int pair_mode, int k0, int nk, int u0, int nu, const void* w_fused, const float* bias,
+                      void* out, void* workspace, void* stream);
 
 /* Config #4 (original CB-Whisper classifier): bilinear resize of the layer-wise similarity images of
  * ragged keywords to the classifier's fixed input size (replaces torchvision resize(..., antialias=False)

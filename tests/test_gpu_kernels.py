@@ -639,3 +639,57 @@ def test_sim_stem_fused_channel_groups(ops, cuda_dev, Cc, K, U, Tk, Tu, multi):
         if hooks:
             lib.kws_debug_set_fused_multi(12, 2, 2)
             lib.kws_debug_set_fused_reduce(1)
+
+
+# ---- fused similarity + stem + max-pool ------------------------------------------------
+@pytest.mark.parametrize("Cc,K,U,Tk,Tu,Dk,ragged", [
+    (12, 3, 2, 150, 1500, 64, False),  # the bench's instance (S12), 13 column tiles of 29 pooled columns
+    (12, 9, 3, 150, 300, 64, True),    # S12 + keyword length table
+    (3, 2, 2, 22, 70, 64, False),      # generic 16-row instance, one column tile
+    (3, 7, 2, 37, 130, 64, True),      # odd Ho (19), odd Wo (65), ragged
+    (4, 2, 2, 150, 300, 384, False),   # L variant: 48-row chunks
+    (4, 6, 2, 150, 200, 384, True),
+    (5, 2, 3, 75, 251, 128, False),    # 32-row chunks, Wo = 126 -> Wp = 63 = 2 full tiles + 5 columns
+    (5, 6, 2, 75, 251, 128, True),
+    (1, 1, 1, 1, 1, 64, False),        # 1 x 1 image
+    (2, 1, 1, 150, 122, 64, False),
+    (8, 1, 1, 9, 123, 64, False),
+    (32, 3, 2, 75, 750, 64, False),    # multi-pass (12 + 12 + 8 layers): partial sums in the workspace, last pass pools
+    (32, 5, 2, 75, 300, 64, True),
+    (16, 40, 5, 30, 260, 64, True),    # multi-pass, more items than SMs
+    (12, 40, 5, 30, 260, 64, False),   # more items than SMs (persistent loop, carried rows reset per item)
+])
+def test_sim_stem_pool_is_maxpool_of_the_fused_stem(ops, cuda_dev, Cc, K, U, Tk, Tu, Dk, ragged):
+    """kws_sim_stem_pool == kws_maxpool_nhwc(kws_sim_stem_ragged(..., bf16 channels-last)), bit for bit (the maximum
+    commutes with the monotone bf16 rounding and both run the same MMAs), == F.max_pool2d(3, 2, 1) of it."""
+    g = gen(cuda_dev)
+    kn = unit_rows(Cc, K, Tk, Dk, g=g, dev=cuda_dev).half()
+    un = unit_rows(Cc, U, Tu, Dk, g=g, dev=cuda_dev).half()
+    un[:, -1, (2 * Tu) // 3:] = 0
+    lens = None
+    if ragged:
+        lens = torch.randint(0, Tk + 1, (K,), generator=g, device=cuda_dev, dtype=torch.int32)
+        lens[0] = 0
+        lens[1] = 1
+        if K > 2:
+            lens[2] = Tk
+        if K > 3:
+            lens[3] = min(Tk, 6)
+        for k in range(K):
+            kn[:, k, int(lens[k]):] = 0
+    sd = {k: v.to(cuda_dev) for k, v in O.make_weights("L", Cc, 64, seed=23).items()}
+    wf, bias = pack_stem_fused(ops, sd)
+    full = ops.sim_stem(kn, un, wf, bias, ops.STEM_OUT_NHWC_BF16, kwd_len=lens)
+    exp = ops.maxpool_nhwc(full)
+    assert torch.equal(exp.float(), torch.nn.functional.max_pool2d(full.float(), 3, 2, 1))
+    Hp, Wp = exp.shape[2], exp.shape[3]
+    buf = torch.full((K * U * 64 * Hp * Wp + 64,), float("nan"), dtype=torch.bfloat16, device=cuda_dev)
+    got = ops.sim_stem_pool(kn, un, wf, bias, out=buf, kwd_len=lens)
+    assert got.shape == exp.shape
+    assert not torch.isnan(got.float()).any(), "pooled rows left unwritten"
+    assert torch.isnan(buf[K * U * 64 * Hp * Wp:].float()).all(), "wrote beyond the pooled activation"
+    assert torch.equal(got, exp)
+    if K >= 3:  # a sub-range of the pair grid into the front of a reused buffer
+        buf.fill_(float("nan"))
+        blk = ops.sim_stem_pool(kn, un, wf, bias, out=buf, k_range=(1, K), u_range=(U - 1, U), kwd_len=lens)
+        assert torch.equal(blk, exp.view(K, U, *exp.shape[1:])[1:K, U - 1:U].flatten(0, 1))

@@ -286,3 +286,20 @@ def test_score_host_streams_slabs_and_matches_score(built_lib, cuda_dev, name):
         assert err(lg, outs["logits"]) <= TOL
         clear = (sc0 - 0.5).abs() > 1e-3
         assert torch.equal(det[clear], det0[clear])
+
+
+@pytest.mark.parametrize("name", ["LE_small", "LEF_odd", "L_small"])
+def test_fused_pool_scoring_is_bit_identical_to_the_separate_maxpool(built_lib, cuda_dev, name):
+    """b200_fused_pool (kws_sim_stem_pool: MaxPool2d(3,2,1) inside the fused kernel) vs the stem activation in HBM +
+    kws_maxpool_nhwc: the body sees the same bf16 tensor, so logits, scores and detections are equal bit for bit --
+    through score(), the batched step and forward(return_features=False)."""
+    m, meta, x, outs, _ = build(name, cuda_dev, b200_body_dtype="bfloat16", b200_return_features=False)
+    assert m.b200_fused_pool
+    a = m.score(x["kwd"], x["utt"], x["km"], x["um"], hotword_mask=x["hot"], max_pairs=5)
+    ra = m(kwd_features=x["kwd"], utt_features=x["utt"][:1], kwd_mask=x["km"], utt_mask=x["um"][:1]).logits
+    m.b200_fused_pool = False
+    b = m.score(x["kwd"], x["utt"], x["km"], x["um"], hotword_mask=x["hot"], max_pairs=5)
+    rb = m(kwd_features=x["kwd"], utt_features=x["utt"][:1], kwd_mask=x["km"], utt_mask=x["um"][:1]).logits
+    for t, u in zip(a, b):
+        assert torch.equal(t, u)
+    assert torch.equal(ra, rb)

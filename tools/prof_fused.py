@@ -22,6 +22,12 @@ from enhance_cb_whisper_b200 import ops  # noqa: E402
 SHAPES = {"cfg2": (12, 64, 150, 1500), "cfg1": (4, 384, 150, 1500), "cfg3": (32, 64, 75, 750)}
 
 
+def _lib_ws(C, pairs, Tk, Tu):
+    from enhance_cb_whisper_b200 import _lib
+
+    return int(_lib.load().kws_sim_stem_pool_workspace_bytes(C, pairs, Tk, Tu))
+
+
 def timeit(fn, n):
     fn()
     torch.cuda.synchronize()
@@ -40,6 +46,7 @@ def main():
     ap.add_argument("--pairs-k", type=int, default=74)
     ap.add_argument("--utts", type=int, default=2)
     ap.add_argument("--iters", type=int, default=2)
+    ap.add_argument("--pool", action="store_true", help="also time the fused stem+max-pool kernel against stem + kws_maxpool_nhwc")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     g = torch.Generator(device=dev).manual_seed(7)
@@ -69,6 +76,14 @@ def main():
     fl = (2.0 * 64 * 49 * Cc * Ho * Wo + 2.0 * Cc * Tk * Tu * Dk) * K * U
     print(f"fused {a.what} C={Cc} Dk={Dk} {Tk}x{Tu}, {K * U} pairs: {t:.3f} ms -> {K * U / t * 1e3:.0f} pairs/s, "
           f"{fl / t / 1e9:.1f} TFLOP/s algorithmic ({fl / t / 1e9 / 1364.9:.3f} of sustained)")
+    if a.pool:  # A/B of SURVEY 8f row 3: stem + separate max-pool kernel vs the fused stem+pool kernel
+        Hp, Wp = (Ho + 1) // 2, (Wo + 1) // 2
+        pooled = torch.empty(K * U, Hp, Wp, 64, dtype=torch.bfloat16, device=dev)
+        tm = timeit(lambda: ops.maxpool_nhwc(out.permute(0, 3, 1, 2), out=pooled), a.iters)
+        ws = torch.empty(max(1, _lib_ws(Cc, K * U, Tk, Tu)), dtype=torch.uint8, device=dev)
+        tp = timeit(lambda: ops.sim_stem_pool(kn, un, wp, bias, out=pooled, workspace=ws), a.iters)
+        print(f"  stem {t:.3f} ms + kws_maxpool_nhwc {tm:.3f} ms = {t + tm:.3f} ms ({K * U / (t + tm) * 1e3:.0f} pairs/s to the "
+              f"pooled activation)  vs  kws_sim_stem_pool {tp:.3f} ms ({K * U / tp * 1e3:.0f} pairs/s): x{(t + tm) / tp:.3f}")
 
 
 if __name__ == "__main__":
