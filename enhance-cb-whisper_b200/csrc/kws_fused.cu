@@ -139,7 +139,8 @@ struct FusedParams {
   int Hp, Wp;      // pooled image: ceil(Ho / 2) x ceil(Wo / 2)
   int whatif;    // development what-if switches (KWS_DEBUG_HOOKS builds only; results are WRONG when set): 1 epilogue
                  // releases the accumulator at once and does nothing else | 2 no half-b shift (no mailbox, no shuffles) |
-                 // 4 no TMA store | 8 stem issues kernel row 0 only | 16 similarity issues one of four k-steps
+                 // 4 no TMA store | 8 stem issues kernel row 0 only | 16 similarity issues one of four k-steps |
+                 // 32 only half of every utterance tile is loaded (half the L2 -> SM operand bytes)
   long long* dbg;  // optional [grid][16] cycle counters (issuer 0-4, epilogue 5-7, converter 8-11; development aid), or null
 };
 
@@ -382,7 +383,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
               mbar_wait(&oempty[stage], phase ^ 1, 100 + stage);
               KWS_TRACE(3, tr_stage, 2);  // slot free seen by the producer
               uint8_t* sa = s_ops + stage * G_STAGE;
-              mbar_arrive_expect_tx(&ofull[stage], G_STAGE);
+              mbar_arrive_expect_tx(&ofull[stage], KWS_WHATIF(32) ? G_STAGE - G_A_BYTES / 2 : G_STAGE);
               tma_load_3d(&map_utt, &ofull[stage], sa, kb * 64, jbase, (p.c0 + c) * p.U + w.u);
               tma_load_3d(&map_kwd, &ofull[stage], sa + G_A_BYTES, kb * 64, ROWS * n - 3, (p.c0 + c) * p.K + w.kw);
               KWS_TRACE(3, tr_stage, 3);  // loads issued
@@ -1306,7 +1307,7 @@ static int sim_stem_core(const void* kwd_n, const void* utt_n, const int32_t* kw
     const uint64_t u_bank = pair_mode == KWS_PAIRS_PER_KEYWORD ? (uint64_t)K * U : (uint64_t)U;
     const uint64_t dims[3] = {(uint64_t)Dk, (uint64_t)Tu, (uint64_t)C * u_bank};
     const uint64_t strides[2] = {(uint64_t)Dk * 2, (uint64_t)Dk * 2 * (uint64_t)Tu};
-    const uint32_t box[3] = {64, 128, 1};
+    const uint32_t box[3] = {64, (g_fused_whatif & 32) ? 64u : 128u, 1};  // what-if 32: half the utterance tile's L2 reads
     if (int e = make_tensor_map(&mu, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, utt_n, dims, strides, box,
                                 CU_TENSOR_MAP_SWIZZLE_128B))
       return e;

@@ -46,6 +46,7 @@ def main():
     ap.add_argument("--pairs-k", type=int, default=74)
     ap.add_argument("--utts", type=int, default=2)
     ap.add_argument("--iters", type=int, default=2)
+    ap.add_argument("--ab-pairs", action="store_true", help="mlp*: A/B of the CTA-pair W1 multicast (debug-hooks library)")
     ap.add_argument("--pool", action="store_true", help="also time the fused stem+max-pool kernel against stem + kws_maxpool_nhwc")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -60,10 +61,23 @@ def main():
         b1 = torch.randn(Cc, H, generator=g, device=dev) * 0.1
         b2 = torch.randn(Cc, P, generator=g, device=dev) * 0.1
         mask = torch.ones(K, Cc, T, device=dev)
-        t = timeit(lambda: ops.mlp_fused(x, list(range(Cc)), w1, b1, w2, b2, mask, ops.MLP_OUT_NORM_F16), a.iters)
         fl = 2.0 * Cc * K * T * (D * H + H * P)
         by = x.numel() * 4 + Cc * K * T * P * 2
-        print(f"mlp_fused {K}x{Cc}x{T}x{D}: {t:.3f} ms -> {fl / t / 1e9:.1f} TFLOP/s, {by / t / 1e6:.0f} GB/s")
+        modes = [None]
+        if a.ab_pairs:  # same-run A/B of the CTA-pair W1 multicast (needs tools/experiments/mlp_cta_pairs_*.patch applied
+            # and the debug flavour: KWS_B200_LIB=..._dbg.so)
+            from enhance_cb_whisper_b200 import _lib
+            modes = [0, 1, 0, 1]
+        ref = None
+        for md in modes:
+            if md is not None:
+                _lib.load().kws_debug_set_mlp_pairs(md)
+            t = timeit(lambda: ops.mlp_fused(x, list(range(Cc)), w1, b1, w2, b2, mask, ops.MLP_OUT_NORM_F16), a.iters)
+            out = ops.mlp_fused(x, list(range(Cc)), w1, b1, w2, b2, mask, ops.MLP_OUT_NORM_F16)
+            same = "" if ref is None else f" bit-identical to the first mode: {bool(torch.equal(out, ref))}"
+            ref = out if ref is None else ref
+            print(f"mlp_fused {K}x{Cc}x{T}x{D}{'' if md is None else f' pairs={md}'}: {t:.3f} ms -> {fl / t / 1e9:.1f} TFLOP/s "
+                  f"({fl / t / 1e9 / 1364.9:.3f} of sustained), {by / t / 1e6:.0f} GB/s ({by / t / 1e6 / 6554.2:.3f} of HBM peak){same}")
         return
     Cc, Dk, Tk, Tu = SHAPES[a.what]
     K, U = a.pairs_k, a.utts

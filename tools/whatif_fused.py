@@ -26,9 +26,9 @@ wp, bias = ops.pack_stem_fused(torch.randn(64, Cc, 7, 7, generator=g, device=dev
 out = torch.empty(K * U, (Tk + 1) // 2, (Tu + 1) // 2, 64, dtype=torch.bfloat16, device=dev)
 lib = _lib.load()
 run = lambda: ops.sim_stem(kn, un, wp, bias, ops.STEM_OUT_NHWC_BF16, out=out)
-combos = [0, 1, 2, 4, 2 | 4, 8, 16, 8 | 16, 1 | 8, 1 | 16, 1 | 8 | 16, 0]
+combos = [0, 32, 32 | 1, 32 | 8 | 16, 32 | 1 | 8 | 16, 1 | 8 | 16, 0] if os.environ.get('KWS_WHATIF_L2') else [0, 1, 2, 4, 2 | 4, 8, 16, 8 | 16, 1 | 8, 1 | 16, 1 | 8 | 16, 0]
 if Cc > 12:
-    combos = [0, 2, 8, 16, 8 | 16, 0]  # multi-pass: the epilogue's partial-sum protocol must stay intact
+    combos = [0, 32, 2, 32 | 2, 0] if os.environ.get('KWS_WHATIF_L2') else [0, 2, 8, 16, 8 | 16, 0]  # multi-pass: the epilogue's partial-sum protocol must stay intact
 for bits in combos:
     lib.kws_debug_set_fused_whatif(bits)
     run()
