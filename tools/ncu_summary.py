@@ -25,6 +25,9 @@ KEYS = [
     "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
     "sm__inst_executed.sum", "smsp__inst_executed.sum", "sm__sass_inst_executed_op_shared_st.sum",
     "smsp__cycles_active.avg", "sm__ctas_launched.sum",
+    # the counters that DO track tcgen05.mma occupancy on sm_100 (the *_realtime variants read "no data" / far too low)
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
     # L2 -> SM fabric: what the fused kernel's operand pipeline is bound by
     "l1tex__m_xbar2l1tex_read_bytes.sum", "lts__t_sector_hit_rate.pct", "lts__t_requests_srcunit_tex.sum",
     "lts__t_sectors_srcunit_tex.sum",
