@@ -76,3 +76,61 @@ def distributed_topk(local: torch.Tensor, k: int, K: int, topk_fn: Callable, gro
     # -1 ids would win ties against real ids at -inf only; map them past every real id
     iall = torch.where(iall < 0, torch.full_like(iall, 2 ** 31 - 1), iall)
     return topk_fn(vall, kk, iall, 0)
+
+
+# ---- length-aware sharding (ragged keyword banks) ---------------------------------------------------------
+# With the keyword length table carried into the fused kernel (kws_sim_stem_ragged) a keyword costs roughly its number of
+# valid frames, so a contiguous split of a vocabulary that is ordered by anything correlated with length (alphabetical
+# lists are) leaves ranks unevenly loaded.  SURVEY.md section 8e: sort / bucket keywords by length before sharding.
+def length_balanced_shards(lengths: torch.Tensor, world: int) -> List[torch.Tensor]:
+    """Partition range(K) into ``world`` shards of (almost) equal size AND equal total length: keywords are sorted
+    by length (longest first, stable) and dealt to the ranks in snake order (0..w-1, w-1..0, ...); each shard is
+    returned as ascending global keyword ids (int64), so that the local order is still the global order and the
+    lower-id tie-break of ``ops.topk`` is preserved.  Shard sizes differ by at most one, total lengths by at most
+    the longest keyword."""
+    K = int(lengths.numel())
+    order = torch.argsort(lengths.reshape(-1).to(torch.int64).cpu(), descending=True, stable=True)
+    pos = torch.arange(K)
+    rnd, col = pos // world, pos % world
+    owner = torch.where(rnd % 2 == 0, col, world - 1 - col)
+    return [torch.sort(order[owner == r]).values for r in range(world)]
+
+
+def gather_scores_indexed(local: torch.Tensor, shards: List[torch.Tensor], group=None) -> torch.Tensor:
+    """local [len(shards[rank]), U] scores of this rank's (non-contiguous) shard -> full [K, U] in global keyword
+    order on every rank."""
+    world = dist.get_world_size(group)
+    K = sum(int(s.numel()) for s in shards)
+    kmax = max(int(s.numel()) for s in shards)
+    U = local.shape[1]
+    pad = local.new_zeros((kmax, U))
+    pad[: local.shape[0]] = local
+    buf = local.new_empty((world * kmax, U))
+    dist.all_gather_into_tensor(buf, pad.contiguous(), group=group)
+    out = local.new_empty((K, U))
+    for r, s in enumerate(shards):
+        out[s.to(local.device)] = buf[r * kmax: r * kmax + int(s.numel())]
+    return out
+
+
+def distributed_topk_indexed(local: torch.Tensor, k: int, shards: List[torch.Tensor], topk_fn: Callable, group=None):
+    """``distributed_topk`` for non-contiguous shards: the global keyword id of local row i is shards[rank][i]."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    K = sum(int(s.numel()) for s in shards)
+    kk = min(k, K)
+    U = local.shape[1]
+    my = shards[rank].to(local.device, torch.int32)
+    assert local.shape[0] == my.numel(), "local shard does not match its id list"
+    vp = local.new_full((kk, U), float("-inf"))
+    ip = torch.full((kk, U), 2 ** 31 - 1, dtype=torch.int32, device=local.device)
+    if local.shape[0] > 0:
+        ids = my.view(-1, 1).expand(-1, U).contiguous()
+        v, i = topk_fn(local.contiguous(), min(kk, local.shape[0]), ids, 0)
+        vp[: v.shape[0]] = v
+        ip[: i.shape[0]] = torch.where(i < 0, torch.full_like(i, 2 ** 31 - 1), i)
+    vall = local.new_empty((world * kk, U))
+    iall = torch.empty((world * kk, U), dtype=torch.int32, device=local.device)
+    dist.all_gather_into_tensor(vall, vp.contiguous(), group=group)
+    dist.all_gather_into_tensor(iall, ip.contiguous(), group=group)
+    return topk_fn(vall, kk, iall, 0)

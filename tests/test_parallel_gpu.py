@@ -59,9 +59,16 @@ def _worker(rank, world, port, variant, q):
         tv, ti = parallel.distributed_topk(sc_l, 5, K, ops.topk)
         sc_1, det_1, _ = m.score(kwd, utt, km, um, hotword_mask=hot, max_pairs=3)  # the whole job on this GPU alone
         ev, ei = ops.topk(sc_1.contiguous(), 5)
-        q.put((rank, bool(torch.equal(gathered, sc_1)), bool(torch.equal(det_g, det_1)), bool(torch.equal(tv, ev)),
+        # length-balanced (non-contiguous) shards, SURVEY 8e: same results through the indexed gather / top-k
+        shards = parallel.length_balanced_shards(km[:, 0].sum(dim=1).cpu(), world)
+        mine = shards[rank].to(dev)
+        sc_b, _, _ = m.score(kwd[mine].contiguous(), utt, km[mine].contiguous(), um, hotword_mask=hot[mine], max_pairs=3)
+        gathered_b = parallel.gather_scores_indexed(sc_b, shards)
+        bv, bi = parallel.distributed_topk_indexed(sc_b, 5, shards, ops.topk)
+        bal_ok = bool(torch.equal(gathered_b, sc_1)) and bool(torch.equal(bv, ev)) and bool(torch.equal(bi, ei))
+        q.put((rank, bool(torch.equal(gathered, sc_1)) and bal_ok, bool(torch.equal(det_g, det_1)), bool(torch.equal(tv, ev)),
                bool(torch.equal(ti, ei)), bool(torch.equal(sc_1[7], sc_1[2])),
-               f"max |gathered - single| {float((gathered - sc_1).abs().max()):.3e}; top-k ids {ti.tolist()} vs {ei.tolist()}"))
+               f"length-balanced ok {bal_ok}; max |gathered - single| {float((gathered - sc_1).abs().max()):.3e}; top-k ids {ti.tolist()} vs {ei.tolist()}"))
     except Exception as exc:  # surface the worker's error in the parent's assertion message
         import traceback
 
