@@ -410,16 +410,13 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
         const ItemShape sh = item_shape<RAGGED>(p, L_next);
         L_next = item_len<RAGGED>(p, it + gridDim.x);
         const int n_chunks = (sh.nQ + QPC - 1) / QPC;
-        for (int n = 0; n < n_chunks; ++n, ++g) {
-          if (ROWS * n - 3 >= sh.L) {
-            // all-zero chunk: no operands, no MMAs; keep the tile hand-shake (the converters write zeros without
-            // reading the tiles)
-            for (int j = 0; 2 * j < kC; ++j) {
-              mbar_wait(&sempty[j], (g & 1) ^ 1, 500 + j);
-              umma_commit(&sfull[j]);
-            }
-            continue;
-          }
+        for (int n = 0; n < n_chunks; ++n) {
+          // All-zero chunk (entirely below the image / the keyword): no operands, no MMAs and NO tile hand-shake -- the
+          // converters know the same thing from the same shape and write zeros without touching the tile barriers, so
+          // the chunk counter g counts real chunks only.  (With the hand-shake kept, the next item's first chunk could
+          // not start before the converters had reached the zero chunk, i.e. finished storing the chunk before it:
+          // a start-up bubble of ~1.5 steps per item on 75-row images.)
+          if (ROWS * n - 3 >= sh.L) continue;
           for (int st = 0; st < stages_per_chunk; ++st) {
             const int c = st / kNkb, kb = st - c * kNkb;
             // the converters have pulled the previous chunk's tiles of this layer pair out of TMEM
@@ -447,6 +444,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
             if (kb == kNkb - 1 && ((c & 1) == 1 || c == kC - 1)) umma_commit(&sfull[c >> 1]);
             if (st == stages_per_chunk - 1) KWS_TRACE(2, g, 5);
           }
+          ++g;
         }
       }
     }
@@ -971,8 +969,9 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
     for (long long it = blockIdx.x; it < p.num_items; it += gridDim.x) {
       const ItemShape sh = item_shape<RAGGED>(p, L_next);
       L_next = item_len<RAGGED>(p, it + gridDim.x);
-      for (int q0 = 0; q0 < sh.nQ; q0 += QPC, ++g) {
+      for (int q0 = 0; q0 < sh.nQ; q0 += QPC) {
         const int nq = sh.nQ - q0 < QPC ? sh.nQ - q0 : QPC;
+        const bool zero_chunk = 4 * q0 - 3 >= sh.L;  // entirely below the image / keyword: not computed, no hand-shake
         const long long c0 = KWS_CLK();
         const long long c1 = c0;
         if (warp == 8 && lane == 0) KWS_TRACE(2, g, 0);
@@ -981,9 +980,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
         uint32_t h2[ROWS][NPAIR];  // [row][layer pair] fp16x2
 #pragma unroll
         for (int j = 0; j < NPAIR; ++j) {
-          if (2 * j < kC && 4 * q0 - 3 >= sh.L) {  // chunk entirely below the image / keyword: zeros, tiles untouched
-            mbar_wait(&sfull[j], g & 1, 700 + j);
-            mbar_arrive(&sempty[j]);
+          if (zero_chunk) {
 #pragma unroll
             for (int r = 0; r < ROWS; ++r) h2[r][j] = 0u;
           } else if (2 * j < kC) {
@@ -1061,6 +1058,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
             for (int j = 0; j < NPAIR; ++j) h2[r][j] = h2[r + 16][j];
         }
         }
+        if (!zero_chunk) ++g;
       }
     }
     if (p.dbg && warp == 8 && lane == 0) {
@@ -1152,7 +1150,9 @@ KWS_KNOB g_multi_group = 12;
 KWS_KNOB g_multi_nh = 2;
 KWS_KNOB g_multi_prefetch = 2;
 KWS_KNOB g_multi_reduce = 1;       // middle passes: TMA reduce-add store (1) | load + add + store (0)
-KWS_KNOB g_multi_small_first = 0;  // remainder group first (no measurable difference; kept as a variant)
+KWS_KNOB g_multi_small_first = 0;
+KWS_KNOB g_multi_last_pf1 = 1;     // last pass of <= 8 layers (28 KB of weights less): partial sums of step n+1 are loaded into a
+                                   // second staging set during step n (+4 % at cfg3: profiles/r02_zero_chunk.log); dense un-pooled only  // remainder group first (no measurable difference; kept as a variant)
 #ifdef KWS_DEBUG_HOOKS
 extern "C" void kws_debug_set_fused_whatif(int bits) { g_fused_whatif = bits; }
 extern "C" void kws_debug_set_fused_s12(int on) { g_fused_s12 = on ? 1 : 0; }
@@ -1164,6 +1164,7 @@ extern "C" void kws_debug_set_fused_grid_limit(int n) { g_fused_grid_limit = n; 
 extern "C" void kws_debug_set_fused_counters(long long* dev_buf) { g_fused_dbg = dev_buf; }
 extern "C" void kws_debug_set_fused_reduce(int on) { g_multi_reduce = on ? 1 : 0; }
 extern "C" void kws_debug_set_fused_small_first(int on) { g_multi_small_first = on ? 1 : 0; }
+extern "C" void kws_debug_set_fused_last_pf1(int on) { g_multi_last_pf1 = on ? 1 : 0; }
 // NOTE: weights must be re-packed (kws_pack_stem_fused) after changing the group size or order.
 extern "C" void kws_debug_set_fused_multi(int group, int nh, int prefetch) {
   g_multi_group = group == 12 ? 12 : 8;
@@ -1396,6 +1397,7 @@ static int sim_stem_core(const void* kwd_n, const void* utt_n, const int32_t* kw
     if (p.acc_mode != 0) {
       KWS_CHECK_ARG(rows == 16 && nh, "sim_stem: internal: multi-pass needs 16-row chunks, bf16 output");
       p.prefetch = g_multi_prefetch;
+      if (g_multi_last_pf1 && p.acc_mode == 3 && Cg <= 8 && !ragged && !pool_pass) p.prefetch = 1;
       if (ragged)
         kern = s12 ? kws_fused_kernel<true, 16, true, 2, true, true> : kws_fused_kernel<true, 16, true, 2, false, true>;
       else

@@ -42,3 +42,17 @@ for bits in combos:
     ms = e0.elapsed_time(e1) / 3
     print(f"{what} whatif={bits:2d}: {ms:.3f} ms -> {K * U / ms * 1e3:.0f} pairs/s", flush=True)
 lib.kws_debug_set_fused_whatif(0)
+if Cc > 12 and Cc % 12 != 0 and Cc % 12 <= 8:  # last pass of <= 8 layers: second staging set + one-step-ahead partial-sum loads
+    for on in (0, 1, 0, 1):
+        lib.kws_debug_set_fused_last_pf1(on)
+        run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        for _ in range(3):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        print(f"{what} last-pass prefetch into a second staging set = {on}: {ms:.3f} ms -> {K * U / ms * 1e3:.0f} pairs/s", flush=True)
+    lib.kws_debug_set_fused_last_pf1(0)
