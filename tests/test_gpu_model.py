@@ -303,3 +303,25 @@ def test_fused_pool_scoring_is_bit_identical_to_the_separate_maxpool(built_lib, 
     for t, u in zip(a, b):
         assert torch.equal(t, u)
     assert torch.equal(ra, rb)
+
+
+def test_hot_path_pooled_output_fused_and_unfused_agree(built_lib, cuda_dev):
+    """engine.hot_path(STEM_OUT_POOL_NHWC_BF16): the fused kernel's pooled activation vs the fallback for shapes the fused
+    kernel does not cover (kws_sim -> kws_stem -> kws_maxpool_nhwc, forced here): same shape, same values up to the fp32
+    summation order of the two stem kernels before the bf16 rounding."""
+    from enhance_cb_whisper_b200 import ops
+
+    m, meta, x, outs, _ = build("LE_small", cuda_dev, b200_body_dtype="bfloat16", b200_return_features=False)
+    eng = m.prepare(cuda_dev)
+    kn, un = eng.compress(x["kwd"], x["km"]), eng.compress(x["utt"], x["um"])
+    got = {}
+    eng.hot_path(kn, un, ops.STEM_OUT_POOL_NHWC_BF16, 4, lambda k0, k1, u0, u1, st: got.__setitem__(("f", k0, u0), st.float().clone()))
+    eng.fused = lambda *a, **k: False
+    eng.hot_path(kn, un, ops.STEM_OUT_POOL_NHWC_BF16, 4, lambda k0, k1, u0, u1, st: got.__setitem__(("u", k0, u0), st.float().clone()))
+    keys = [k for k in got if k[0] == "f"]
+    assert keys
+    Ho, Wo = (meta["Tk"] + 1) // 2, (meta["Tu"] + 1) // 2
+    for _, k0, u0 in keys:
+        a, b = got[("f", k0, u0)], got[("u", k0, u0)]
+        assert a.shape == b.shape and a.shape[2:] == ((Ho + 1) // 2, (Wo + 1) // 2)
+        assert (a - b).abs().max().item() <= 2e-2 * max(1.0, b.abs().max().item() / 4)

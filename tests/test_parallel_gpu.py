@@ -65,10 +65,16 @@ def _worker(rank, world, port, variant, q):
         sc_b, _, _ = m.score(kwd[mine].contiguous(), utt, km[mine].contiguous(), um, hotword_mask=hot[mine], max_pairs=3)
         gathered_b = parallel.gather_scores_indexed(sc_b, shards)
         bv, bi = parallel.distributed_topk_indexed(sc_b, 5, shards, ops.topk)
-        bal_ok = bool(torch.equal(gathered_b, sc_1)) and bool(torch.equal(bv, ev)) and bool(torch.equal(bi, ei))
+        # a different grouping of keywords into body batches: the library convolutions are deterministic per batch but not
+        # bit-stable across batch compositions (observed: 4e-7), so the non-contiguous shards are held to 1e-5 and to the
+        # same top-k ids; the contiguous shards above cut on block boundaries and ARE bit-identical
+        bal_ok = (float((gathered_b - sc_1).abs().max()) <= 1e-5 and float((bv - ev).abs().max()) <= 1e-5
+                  and bool(torch.equal(bi, ei)))
+        bal_info = (f"balanced: scores {bool(torch.equal(gathered_b, sc_1))} (max diff {float((gathered_b - sc_1).abs().max()):.3e}), "
+                    f"top-k vals {bool(torch.equal(bv, ev))}, ids {bool(torch.equal(bi, ei))}; shards {[s.tolist() for s in shards]}; ")
         q.put((rank, bool(torch.equal(gathered, sc_1)) and bal_ok, bool(torch.equal(det_g, det_1)), bool(torch.equal(tv, ev)),
                bool(torch.equal(ti, ei)), bool(torch.equal(sc_1[7], sc_1[2])),
-               f"length-balanced ok {bal_ok}; max |gathered - single| {float((gathered - sc_1).abs().max()):.3e}; top-k ids {ti.tolist()} vs {ei.tolist()}"))
+               bal_info + f"max |gathered - single| {float((gathered - sc_1).abs().max()):.3e}; top-k ids {ti.tolist()} vs {ei.tolist()}"))
     except Exception as exc:  # surface the worker's error in the parent's assertion message
         import traceback
 
