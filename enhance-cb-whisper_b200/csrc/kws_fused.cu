@@ -123,7 +123,7 @@ struct FusedParams {
   int acc_mode;  // 0 single pass | 1 first pass: write fp16 partial sums | 2 middle: += | 3 last: +=, bias, ReLU, bf16
   int reduce_mid;  // middle passes add their partial sums with a TMA reduce-add store (fp16 add in L2) instead of
                    // loading the previous sums, adding in registers and storing
-  int n_mma;     // stem MMAs per kernel row: 2 (C <= 8) or 3
+  int n_mma;     // stem MMAs per kernel row: 1 (C <= 4: the Y' MMA alone), 2 (C <= 8) or 3
   int nP;        // stem steps per item = ceil(Ho / 2)
   int nQ;        // quanta (4 input rows) converted per item = nP + 2
   int n_chunks;  // similarity chunks (ROWS input rows = ROWS/4 quanta) per item
@@ -505,6 +505,13 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
             // block [k8][rp][plane]: rp = (di+1)&1; byte offsets in 16-byte units
             const uint32_t row16 = ((((di + 1) & 1) * 2 * G_BLOCK) >> 4) + slot0 * 64;
             const uint64_t b_row = bdesc0 + (uint64_t)((di * n_mma * G_MMA_W_BYTES) >> 4);
+            if (n_mma == 1) {
+              // up to 4 layers: (Y' plane0 | Y' plane1) carries channels 0..3 of all seven taps -- ONE MMA per kernel row
+              // instead of two half-empty X MMAs (the stem MMAs are what the power-capped kernel spends its energy on)
+              umma_f16(d, adesc_pl + (uint64_t)(row16 + ((4 * G_BLOCK) >> 4)), b_row, idesc_stem, di != 0);
+              if (di == 3) umma_commit(&qempty[(qbase + P) & 3]);
+              continue;
+            }
             // (X plane0 | +1 px): half a taps 0,2; half b taps 4,6
             umma_f16(d, adesc_px + (uint64_t)row16, b_row, idesc_stem, di != 0);
             if (n_mma == 3) {
@@ -962,6 +969,7 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
     const bool has_left = (x >> 1) > 0;  // Y' chunk of the left neighbour (same plane) takes our channels 8..11 too
     const uint32_t t_lane = tmem_base + G_TMEM_SIM + ((uint32_t)(q4 * 32) << 16);
     const bool yp = kNmma == 3;
+    const bool yonly = kNmma == 1;  // up to 4 layers: channels 0..3 travel in the Y' position, the X blocks are not used
     uint32_t g = 0;   // global similarity chunk counter
     uint32_t Gq = 0;  // global quantum counter
     long long tc_sfull = 0, tc_qempty = 0, tc_ld = 0, tc_st = 0;
@@ -1031,10 +1039,13 @@ kws_fused_kernel(const __grid_constant__ CUtensorMap map_utt, const __grid_const
               const uint4 vx = make_uint4(h2[4 * qq + t][0], NPAIR > 1 ? h2[4 * qq + t][NPAIR > 1 ? 1 : 0] : 0u,
                                           NPAIR > 2 ? h2[4 * qq + t][NPAIR > 2 ? 2 : 0] : 0u,
                                           NPAIR > 3 ? h2[4 * qq + t][NPAIR > 3 ? 3 : 0] : 0u);
-              *reinterpret_cast<uint4*>(d0) = vx;
-              if (slot == 0) *reinterpret_cast<uint4*>(d0 + G_NR * 1024) = vx;  // mirror: tap windows never wrap
-              if (NPAIR > 5 && yp) {
-                const uint2 vy = make_uint2(h2[4 * qq + t][NPAIR > 5 ? 4 : 0], h2[4 * qq + t][NPAIR > 5 ? 5 : 0]);
+              if (!yonly) {
+                *reinterpret_cast<uint4*>(d0) = vx;
+                if (slot == 0) *reinterpret_cast<uint4*>(d0 + G_NR * 1024) = vx;  // mirror: tap windows never wrap
+              }
+              if ((NPAIR > 5 && yp) || yonly) {
+                const uint2 vy = yonly ? make_uint2(vx.x, vx.y)
+                                       : make_uint2(h2[4 * qq + t][NPAIR > 5 ? 4 : 0], h2[4 * qq + t][NPAIR > 5 ? 5 : 0]);
                 uint8_t* dy = d0 + 4 * G_BLOCK;
                 *reinterpret_cast<uint2*>(dy) = vy;                    // own chunk, elements 0..3
                 if (has_left) *reinterpret_cast<uint2*>(dy - 8) = vy;  // left neighbour's chunk, elements 4..7
@@ -1088,6 +1099,7 @@ static_assert(g_smem_bytes(16, 3) <= 232448 && g_smem_bytes(32, 2) <= 232448 && 
 //   m = 0            : channels e,      dj = 2*chunk      + 4*half          (X, even plane)
 //   m = n_mma - 1    : channels e,      dj = 1 + 2*chunk  + 4*half          (X, odd plane)
 //   m = 1 (n_mma = 3): channels 8+(e&3), dj = chunk + 2*(e>>2) + 4*half     (Y', chunk = plane)
+//   n_mma = 1 (C <= 4): the Y' layout alone with channels e&3
 // taps dj > 6 and channels >= C are zero.
 __global__ void pack_stem_fused_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
                                        const float* __restrict__ beta, const float* __restrict__ mean,
@@ -1099,7 +1111,9 @@ __global__ void pack_stem_fused_kernel(const float* __restrict__ w, const float*
     const int m = (i >> 11) % n_mma, di = (i >> 11) / n_mma;
     const int half = n >> 6, oc = n & 63;
     int dj, ch;
-    if (m == 0) {
+    if (n_mma == 1) {  // up to 4 layers: the Y' layout with channels 0..3
+      dj = chunk + 2 * (e >> 2) + 4 * half, ch = e & 3;
+    } else if (m == 0) {
       dj = 2 * chunk + 4 * half, ch = e;
     } else if (m == n_mma - 1) {
       dj = 1 + 2 * chunk + 4 * half, ch = e;
@@ -1137,7 +1151,7 @@ KWS_KNOB g_fused_grid_limit = 0;
 KWS_KNOB g_fused_whatif = 0;
 KWS_KNOB g_fused_rows = 0;
 KWS_KNOB g_fused_s12 = 1;  // 12-layer / Dk = 64 compile-time specialisation
-static int fused_n_mma(int C) { return C <= 8 ? 2 : 3; }
+static int fused_n_mma(int C) { return C <= 4 ? 1 : (C <= 8 ? 2 : 3); }
 // C > 12 layers are processed in passes over channel groups of 12 layers; the passes chain their
 // partial sums through the output buffer itself (fp16, same tiles), the last one adds bias + ReLU -> bf16.
 constexpr int G_MAX_C_TOTAL = 64;

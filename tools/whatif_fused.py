@@ -26,7 +26,8 @@ wp, bias = ops.pack_stem_fused(torch.randn(64, Cc, 7, 7, generator=g, device=dev
 out = torch.empty(K * U, (Tk + 1) // 2, (Tu + 1) // 2, 64, dtype=torch.bfloat16, device=dev)
 lib = _lib.load()
 run = lambda: ops.sim_stem(kn, un, wp, bias, ops.STEM_OUT_NHWC_BF16, out=out)
-combos = [0, 32, 32 | 1, 32 | 8 | 16, 32 | 1 | 8 | 16, 1 | 8 | 16, 0] if os.environ.get('KWS_WHATIF_L2') else [0, 1, 2, 4, 2 | 4, 8, 16, 8 | 16, 1 | 8, 1 | 16, 1 | 8 | 16, 0]
+ITERS = int(os.environ.get("KWS_WHATIF_ITERS", "3"))  # >= 300: sustained (power-capped) regime instead of a burst
+combos = [0, 8, 16, 32, 1, 2, 4, 0] if ITERS > 50 else [0, 32, 32 | 1, 32 | 8 | 16, 32 | 1 | 8 | 16, 1 | 8 | 16, 0] if os.environ.get('KWS_WHATIF_L2') else [0, 1, 2, 4, 2 | 4, 8, 16, 8 | 16, 1 | 8, 1 | 16, 1 | 8 | 16, 0]
 if Cc > 12:
     combos = [0, 32, 2, 32 | 2, 0] if os.environ.get('KWS_WHATIF_L2') else [0, 2, 8, 16, 8 | 16, 0]  # multi-pass: the epilogue's partial-sum protocol must stay intact
 for bits in combos:
@@ -35,11 +36,11 @@ for bits in combos:
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
     e0.record()
-    for _ in range(3):
+    for _ in range(ITERS):
         run()
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 3
+    ms = e0.elapsed_time(e1) / ITERS
     print(f"{what} whatif={bits:2d}: {ms:.3f} ms -> {K * U / ms * 1e3:.0f} pairs/s", flush=True)
 lib.kws_debug_set_fused_whatif(0)
 if Cc > 12 and Cc % 12 != 0 and Cc % 12 <= 8:  # last pass of <= 8 layers: second staging set + one-step-ahead partial-sum loads
