@@ -15,11 +15,14 @@ One JSON line on stdout (rank 0).  Records of the line (B200 arm, default worklo
   weak scaling, no data-path collective.
 * ``value_ragged``  the same step with the keyword length table carried into the fused kernel (rows beyond a keyword's
   last frame are provably relu(bias): no similarity, no stem MMAs, constant fill); same output bytes, bit-identical.
+* ``value_pooled``  the same step ending at the MAX-POOLED activation (what ResNetEmbeddings hands to the encoder): the
+  fused similarity + stem + pool kernel (kws_sim_stem_pool; the stem activation never reaches HBM) against the stem
+  activation in HBM + kws_maxpool_nhwc (measured A/B); bit-identical outputs.
 * ``roofline``  the fused kernel: algorithmic FLOPs per launch / CUDA-event duration per launch, against the measured
   sustained bf16 peak of MEASURED_PEAKS.json; ``traffic`` from the committed ncu capture of the same kernel instance.
 * ``e2e``       THE SAME JOB (all K x U pairs) through the reference-facing call ``KWSModelB200.score_host`` from pinned
   HOST buffers to HOST scores / detections / top-10: H2D of the raw keyword bank (slabs, overlapped) + compression into
-  the resident bank, utterances streamed in slabs (H2D overlapped), similarity+stem, max-pool, the ResNet-50 body + head
+  the resident bank, utterances streamed in slabs (H2D overlapped), similarity+stem+max-pool (one kernel), the ResNet-50 body + head
   (third-party arithmetic: cuDNN bf16 fused convolutions), scores, detections, (N > 1: NCCL all-gather + distributed
   top-k), D2H.  ``e2e_parity`` is the same call with the fp32 body (the mode that meets the 2e-3 logit tolerance) on a
   bounded slab of the job.
