@@ -47,6 +47,7 @@ def main():
     ap.add_argument("--utts", type=int, default=2)
     ap.add_argument("--iters", type=int, default=2)
     ap.add_argument("--ab-pairs", action="store_true", help="mlp*: A/B of the CTA-pair W1 multicast (debug-hooks library)")
+    ap.add_argument("--pool-only", action="store_true", help="run only kws_sim_stem_pool (ncu capture of the POOL instance)")
     ap.add_argument("--pool", action="store_true", help="also time the fused stem+max-pool kernel against stem + kws_maxpool_nhwc")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -85,6 +86,13 @@ def main():
     kn, un = unit(Cc, K, Tk, Dk).half(), unit(Cc, U, Tu, Dk).half()
     one, zero = torch.ones(64, device=dev), torch.zeros(64, device=dev)
     wp, bias = ops.pack_stem_fused(torch.randn(64, Cc, 7, 7, generator=g, device=dev) * 0.05, one, zero, zero, one)
+    if a.pool_only:  # just the fused stem + max-pool kernel (for an ncu capture of the POOL instance)
+        Hp, Wp = (Ho + 1) // 2, (Wo + 1) // 2
+        pooled = torch.empty(K * U, Hp, Wp, 64, dtype=torch.bfloat16, device=dev)
+        ws = torch.empty(max(1, _lib_ws(Cc, K * U, Tk, Tu)), dtype=torch.uint8, device=dev)
+        tp = timeit(lambda: ops.sim_stem_pool(kn, un, wp, bias, out=pooled, workspace=ws), a.iters)
+        print(f"fused+pool {a.what}, {K * U} pairs: {tp:.3f} ms -> {K * U / tp * 1e3:.0f} pairs/s")
+        return
     out = torch.empty(K * U, Ho, Wo, 64, dtype=torch.bfloat16, device=dev)
     t = timeit(lambda: ops.sim_stem(kn, un, wp, bias, ops.STEM_OUT_NHWC_BF16, out=out), a.iters)
     fl = (2.0 * 64 * 49 * Cc * Ho * Wo + 2.0 * Cc * Tk * Tu * Dk) * K * U
