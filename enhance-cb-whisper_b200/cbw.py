@@ -104,6 +104,7 @@ class CBWKeywordSpotterB200:
         self.resnet = resnet.eval()
         self.size = tuple(size)
         self.body_dtype = body_dtype
+        self.fused_pool = True  # bf16 body: the stem's max-pool runs inside the fused kernel (kws_sim_stem_pool)
         self._packed = None
         self._packed_fused = None
         self._lowp = None
@@ -126,19 +127,20 @@ class CBWKeywordSpotterB200:
                                                      emb.normalization.running_var.to(device))
         return self._packed_fused
 
-    def _body(self, st):
+    def _body(self, st, pooled: bool = False):
         if self.body_dtype == "float32":
             return run_body(self.resnet, st)
         if self._lowp is None:  # BatchNorms folded + cuDNN fused convolutions (body.py), max-pool in libkws_b200
             self._lowp = FusedBody(self.resnet, torch.bfloat16)
-        return self._lowp(ops.maxpool_nhwc(st), pooled=True)
+        return self._lowp(st if pooled else ops.maxpool_nhwc(st), pooled=True)
 
     @torch.no_grad()
     def stem_fused(self, kwd_n: torch.Tensor, lens: torch.Tensor, utt_i: torch.Tensor, out_mode: int,
                    max_pairs: int = 256, consume=None):
         """Scoring path up to the stem activation, resized image never built.  kwd_n fp16 [C,K,64,D] (pack_keywords),
         lens int32 [K], utt_i fp16 [C,S,Wi,D] (ops.interp_rows to the image width).  Calls
-        ``consume(k0, k1, stem_activation [(k1-k0)*S, 64, Ho, Wo])`` per block of keywords."""
+        ``consume(k0, k1, stem_activation [(k1-k0)*S, 64, Ho, Wo])`` per block of keywords (``out_mode``
+        STEM_OUT_POOL_NHWC_BF16: the max-pooled activation [(k1-k0)*S, 64, ceil(Ho/2), ceil(Wo/2)])."""
         C, K, Tkp, _ = kwd_n.shape
         S = utt_i.shape[1]
         wf, bias = self._weights_fused(kwd_n.device)
@@ -147,7 +149,10 @@ class CBWKeywordSpotterB200:
             k1 = min(K, k0 + kb)
             s_op = ops.sim_operand(kwd_n[:, k0:k1].contiguous() if (k0, k1) != (0, K) else kwd_n, utt_i)
             wy = ops.resize_row_weights(lens[k0:k1].contiguous(), k1 - k0, C, Tkp, self.size[0])
-            st = ops.sim_stem(wy, s_op, wf, bias, out_mode, per_keyword=True)
+            if out_mode == ops.STEM_OUT_POOL_NHWC_BF16:  # + the max-pool behind the stem, in the same kernel
+                st = ops.sim_stem_pool(wy, s_op, wf, bias, per_keyword=True)
+            else:
+                st = ops.sim_stem(wy, s_op, wf, bias, out_mode, per_keyword=True)
             if consume is not None:
                 consume(k0, k1, st)
 
@@ -178,10 +183,11 @@ class CBWKeywordSpotterB200:
             K = kwd_n.shape[1]
             out = torch.empty((K, S, 2), dtype=torch.float32, device=dev)
 
+            pooled = lowp and self.fused_pool
             def consume(k0, k1, st):
-                out[k0:k1] = self._body(st).float().view(k1 - k0, S, 2)
+                out[k0:k1] = self._body(st, pooled).float().view(k1 - k0, S, 2)
 
-            self.stem_fused(kwd_n, lens, utt_i, out_mode, max_pairs, consume)
+            self.stem_fused(kwd_n, lens, utt_i, ops.STEM_OUT_POOL_NHWC_BF16 if pooled else out_mode, max_pairs, consume)
             return out
         _, f16 = similarity_images(kwd_list, utt_hs, self.size, want_f32=False, want_f16=True)
         K, S = f16.shape[:2]

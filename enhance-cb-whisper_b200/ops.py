@@ -377,15 +377,20 @@ def sim_stem_pool_workspace_bytes(Cc: int, pairs: int, Tk: int, Tu: int) -> int:
 def sim_stem_pool(kwd_n: torch.Tensor, utt_n: torch.Tensor, w_fused: torch.Tensor, bias: torch.Tensor,
                   diag: bool = False, out: Optional[torch.Tensor] = None, k_range: Optional[Tuple[int, int]] = None,
                   u_range: Optional[Tuple[int, int]] = None, kwd_len: Optional[torch.Tensor] = None,
-                  workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+                  workspace: Optional[torch.Tensor] = None, per_keyword: bool = False) -> torch.Tensor:
     """Fused similarity + stem + MaxPool2d(3,2,1) (kws_sim_stem_pool): the activation ResNetEmbeddings hands to the
     encoder, bf16 channels_last [N,64,ceil(Ho/2),ceil(Wo/2)]; arguments as sim_stem.  More than 12 layers need a
-    ``workspace`` for the partial sums of the channel-group passes (allocated here when not given)."""
+    ``workspace`` for the partial sums of the channel-group passes (allocated here when not given).  ``per_keyword``:
+    utt_n is [C, K*U, Tu, Dk], one utterance-side operand per (keyword, utterance) (config #4)."""
     lib = _lib.load()
     Cc, K, Tk, Dk = kwd_n.shape
     Cu, U, Tu, Dku = utt_n.shape
     if Cc != Cu or Dk != Dku:
         raise KWSError(f"operand mismatch: kwd {tuple(kwd_n.shape)} vs utt {tuple(utt_n.shape)}")
+    if per_keyword:
+        if diag or kwd_len is not None or U % K != 0:
+            raise KWSError("per_keyword needs utt_n [C, K*U, Tu, Dk], diag=False and no keyword length table")
+        U //= K
     k0, k1 = k_range if k_range is not None else (0, K)
     u0, u1 = u_range if u_range is not None else (0, U)
     pairs = (k1 - k0) if diag else (k1 - k0) * (u1 - u0)
@@ -402,7 +407,8 @@ def sim_stem_pool(kwd_n: torch.Tensor, utt_n: torch.Tensor, w_fused: torch.Tenso
         workspace = torch.empty(need, dtype=torch.uint8, device=kwd_n.device)
     check(lib.kws_sim_stem_pool(_cuda(kwd_n, "kwd_n", torch.float16), _cuda(utt_n, "utt_n", torch.float16),
                                 _cuda(kwd_len, "kwd_len", torch.int32), Cc, K, U, Tk, Tu, Dk,
-                                PAIRS_DIAG if diag else PAIRS_ALL, k0, k1 - k0, u0, u1 - u0,
+                                PAIRS_PER_KEYWORD if per_keyword else (PAIRS_DIAG if diag else PAIRS_ALL), k0, k1 - k0,
+                                u0, u1 - u0,
                                 _cuda(w_fused, "w_fused", torch.float16), _cuda(bias, "bias", torch.float32),
                                 _cuda(out, "out"), _cuda(workspace, "workspace") if need else None, _stream()),
           "kws_sim_stem_pool", launches=(Cc + 11) // 12)

@@ -562,6 +562,13 @@ def test_cbw_keyword_spotter_logits_and_detections(built_lib, cuda_dev):
     margin = (exp[..., 1] - exp[..., 0]).abs().min().item()
     if margin > 1e-2:
         assert det == [torch.nonzero(exp_hit[:, s]).flatten().tolist() for s in range(S)]
+    # bf16 body: the stem's max-pool inside the fused kernel (KWS_PAIRS_PER_KEYWORD + POOL) == stem -> kws_maxpool_nhwc
+    sp16 = cbw.CBWKeywordSpotterB200(resnet.to(cuda_dev), size=size, body_dtype="bfloat16")
+    a16 = sp16.logits([k.to(cuda_dev) for k in kwd_list], utt.to(cuda_dev))
+    sp16.fused_pool = False
+    b16 = sp16.logits([k.to(cuda_dev) for k in kwd_list], utt.to(cuda_dev))
+    assert torch.equal(a16, b16)
+    assert maxerr(a16.cpu(), exp) <= 0.1 * max(1.0, exp.abs().max().item())
 
 
 def test_cbw_matches_reference_fixture(built_lib, cuda_dev):
