@@ -29,7 +29,7 @@ run = lambda: ops.sim_stem(kn, un, wp, bias, ops.STEM_OUT_NHWC_BF16, out=out)
 ITERS = int(os.environ.get("KWS_WHATIF_ITERS", "3"))  # >= 300: sustained (power-capped) regime instead of a burst
 combos = [0, 8, 16, 32, 1, 2, 4, 0] if ITERS > 50 else [0, 32, 32 | 1, 32 | 8 | 16, 32 | 1 | 8 | 16, 1 | 8 | 16, 0] if os.environ.get('KWS_WHATIF_L2') else [0, 1, 2, 4, 2 | 4, 8, 16, 8 | 16, 1 | 8, 1 | 16, 1 | 8 | 16, 0]
 if Cc > 12:
-    combos = [0, 32, 2, 32 | 2, 0] if os.environ.get('KWS_WHATIF_L2') else [0, 2, 8, 16, 8 | 16, 0]  # multi-pass: the epilogue's partial-sum protocol must stay intact
+    combos = [0, 8, 16, 32, 2, 0] if ITERS > 50 else [0, 32, 2, 32 | 2, 0] if os.environ.get('KWS_WHATIF_L2') else [0, 2, 8, 16, 8 | 16, 0]  # multi-pass: the epilogue's partial-sum protocol must stay intact
 for bits in combos:
     lib.kws_debug_set_fused_whatif(bits)
     run()
