@@ -71,6 +71,21 @@ def test_bad_arguments_are_rejected_without_a_device(built_lib):
     assert lib.kws_topk(one, None, 10, 1, 0, 2000, one, one, None, None) == -1
     assert lib.kws_topk(one, None, 5000, 1, 0, 10, one, one, None, None) == -1  # more than one segment: workspace
     assert lib.kws_topk_workspace_bytes(100, 4, 10) == 0 and lib.kws_topk_workspace_bytes(100000, 512, 200) > 0
+    # fused similarity + stem (+ pool): pooled output only through kws_sim_stem_pool; > 12 layers need the workspace
+    args = [one, one, None, 12, 2, 2, 16, 128, 64, 0, 0, 2, 0, 2, one, one]
+    assert lib.kws_sim_stem_ragged(*args, 2, one, None) == -1  # KWS_STEM_OUT_POOL_NHWC_BF16 is not an out_mode here
+    assert b"kws_sim_stem_pool" in lib.kws_last_error()
+    args32 = list(args)
+    args32[3] = 32
+    assert lib.kws_sim_stem_pool(*args32, one, None, None) == -1
+    assert b"workspace" in lib.kws_last_error()
+    assert lib.kws_sim_stem_pool_workspace_bytes(12, 1000, 150, 1500) == 0
+    assert lib.kws_sim_stem_pool_workspace_bytes(32, 1000, 75, 750) == 1000 * 38 * 375 * 64 * 2
+    assert lib.kws_sim_stem_ragged(one, one, one, *args[3:9], 2, *args[10:], 1, one, None) == -1  # keyword lengths x KWS_PAIRS_PER_KEYWORD
+    assert b"length table" in lib.kws_last_error()
+    # fused projector: shapes it does not cover are reported, not mis-computed
+    assert lib.kws_mlp_fused_supported(768, 384, 64) == 1 and lib.kws_mlp_fused_supported(1280, 640, 64) == 1
+    assert lib.kws_mlp_fused_supported(100, 50, 64) == 0 and lib.kws_mlp_fused_supported(768, 384, 24) == 0
     with pytest.raises(_lib.KWSError):
         _lib.check(-1, "kws_topk")
 
