@@ -47,3 +47,26 @@ def test_compress_rejects_wrong_width_and_layer_count():
         e.compress(torch.zeros(1, 2, 4, 32), None)  # D != model embedding_dim
     with pytest.raises(ops.KWSError):
         e.compress(torch.zeros(1, 2, 4, 64), None, layer_idx=[0])  # needs C indices
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.lists(st.integers(min_value=0, max_value=150), min_size=0, max_size=300), st.integers(min_value=1, max_value=8))
+def test_length_balanced_shards_properties(lens, world):
+    """SURVEY 8e load balance: a partition of the vocabulary, shard sizes within one keyword, total valid frames
+    within the longest keyword of each other, ascending ids inside a shard (the top-k tie-break order survives)."""
+    import torch
+
+    from enhance_cb_whisper_b200 import parallel
+
+    lt = torch.tensor(lens, dtype=torch.int64)
+    shards = parallel.length_balanced_shards(lt, world)
+    assert len(shards) == world
+    allids = torch.cat(shards) if shards else torch.empty(0, dtype=torch.int64)
+    assert sorted(allids.tolist()) == list(range(len(lens)))
+    sizes = [int(s.numel()) for s in shards]
+    assert max(sizes) - min(sizes) <= 1
+    for s in shards:
+        assert s.tolist() == sorted(s.tolist())
+    if lens:
+        tot = [int(lt[s].sum()) for s in shards]
+        assert max(tot) - min(tot) <= max(lens)
