@@ -46,7 +46,20 @@
 // Roles (384 threads): warp 0 TMA producer, warp 1 stem MMA issuer, warp 2 TMEM allocator + similarity MMA
 // issuer (one elected thread each: two independent instruction streams into the one tensor pipe, so the
 // barrier polls of one never starve it), warps 4..7 stem epilogue (bf16 results staged in swizzled shared
-// memory, one TMA store per warp and step), warps 8..11 converters.
+// memory, one TMA store per warp and step), warps 8..11 converters.  Warp 3 is idle except in the POOL instances, where it
+// is the pool warp (MaxPool2d(3,2,1) on the staged tile; see the POOL template flag).
+//
+// Template instances (the role loops are sensitive to every instruction, so whatever varies per shape or mode is a
+// template parameter): NHWC (bf16 channels-last via TMA stores | fp32 NCHW, parity), ROWS (similarity chunk height 16 |
+// 32 | 48), MULTI (channel-group passes for more than 12 layers: fp16 partial sums chained through the output tiles),
+// S12 (12 layers x Dk = 64 as compile-time constants), RAGGED (keyword length table: rows beyond a keyword skipped and
+// filled with relu(bias)), POOL (the max-pool behind the stem applied before the activation leaves the SM).
+// Up to 4 layers the stem issues ONE MMA per kernel row (channels 0..3 in the Y' position) instead of two.
+//
+// Two regimes: in bursts the kernel is bound by two loops of ~2 k cycles per step that overlap
+// imperfectly (operands -> similarity -> converters -> ring -> stem MMAs; accumulator -> epilogue -> store); run back to
+// back, as the benchmark does, every shape sits at the 1 kW power cap and throughput is energy per pair, ~45 % of
+// which are the stem MMAs and their shared-memory operands at 12 layers.
 //
 // Budget (C = 12, 150 x 1500): the kernel is bound by the shared-memory port (128 B/clk), which every
 // operand read of an SS-mode MMA goes through.  Per step (2 output rows x 60 px): stem MMA operands
