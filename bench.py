@@ -130,6 +130,30 @@ def flops_per_pair(wl):
     return sim, stem
 
 
+def issued_flops_per_pair(wl):
+    """Tensor-core FLOPs the fused kernel ISSUES per pair (every tcgen05.mma counted at 2 M N K), as opposed to the
+    algorithmic FLOPs of ``flops_per_pair``: 60 of 64 pixel slots per row carry output and the last column tile is partly
+    empty (M), 7 taps x C channels are packed into K = 16 x N = 128 tap-pair MMAs (87.5 % full at 12 layers), the
+    similarity runs per chunk of 16 / 32 / 48 keyword rows (N).  Mirrors csrc/kws_fused.cu: fused_n_mma, chunk heights,
+    channel-group passes; all-zero chunks below the image are not issued."""
+    tk, tu = frames(wl)
+    c_all = wl["C"]
+    dk = wl["D"] if wl["variant"] == "L" else wl["P"]
+    ho, wo = (tk + 1) // 2, (tu + 1) // 2
+    tiles = (wo + 59) // 60
+    n_p = (ho + 1) // 2
+    n_q = n_p + 2
+    groups = [c_all] if c_all <= 12 else [12] * (c_all // 12) + ([c_all % 12] if c_all % 12 else [])
+    stem = sim = 0.0
+    for cg in groups:
+        rows = 16 if len(groups) > 1 else (48 if cg <= 4 else (32 if cg <= 6 else 16))
+        n_mma = 1 if cg <= 4 else (2 if cg <= 8 else 3)
+        stem += tiles * n_p * 7 * n_mma * (2.0 * 128 * 128 * 16)
+        chunks = sum(1 for n in range((n_q + rows // 4 - 1) // (rows // 4)) if rows * n - 3 < tk)
+        sim += tiles * chunks * cg * (dk // 16) * (2.0 * 128 * rows * 16)
+    return sim, stem
+
+
 def flops_projection(wl, n_kw, n_utt):
     if wl["variant"] == "L":
         return 0.0
@@ -627,6 +651,14 @@ def in_scope_record(ctx, wl, wl_name, model, data, steps, warmup, max_pairs, sam
         "frac": achieved / peak, "traffic": None if ragged else roofline_traffic(wl_name, kernel, ppl),
         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if ctx.peaks else "fallback 1400 (of fallback)",
         "flops_per_pair": {"sim": f_sim, "stem": f_stem},
+        # the same launches counted in ISSUED tensor-core FLOPs (padding of the tap-pair / pixel-slot packing included):
+        # how close the kernel runs to the cuBLAS rate under the same power cap; the algorithmic `frac` is this number
+        # times the packing efficiency
+        "issued": (lambda i_sim, i_stem: {
+            "flops_per_pair": {"sim": i_sim, "stem": i_stem},
+            "tflops": (i_sim + i_stem) * sum(npairs) / (kern_ms / 1e3) / 1e12 if kern_ms > 0 else 0.0,
+            "frac": (i_sim + i_stem) * sum(npairs) / (kern_ms / 1e3) / 1e12 / peak if kern_ms > 0 else 0.0,
+            "packing_efficiency": (f_sim + f_stem) / (i_sim + i_stem)})(*issued_flops_per_pair(wl)) if fused else None,
         "launches": len(dur_ms), "avg_launch_ms": kern_ms / max(len(dur_ms), 1), "pairs_per_launch": ppl,
         "share_of_step": kern_ms / steps / ms_step if ms_step > 0 else None,
     }
