@@ -22,6 +22,24 @@ def test_work_per_pair_matches_baseline_md():
     assert abs(bench.flops_projection(wl, wl["K"], wl["U"]) / 1e12 - 4.09) < 0.05
 
 
+def test_issued_flops_account_for_the_kernels_packing():
+    """roofline.issued: every tcgen05.mma of the fused kernel at 2 M N K.  cfg2: 13 column tiles x 38 steps x 21 stem
+    MMAs of 128 x 128 x 16 and 10 chunks x 12 layers x 4 similarity MMAs of 128 x 16 x 16 per tile."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    sim, stem = bench.issued_flops_per_pair(bench.WORKLOADS["cfg2"])
+    assert stem == 13 * 38 * 21 * 2.0 * 128 * 128 * 16
+    assert sim == 13 * 10 * 12 * 4 * 2.0 * 128 * 16 * 16
+    for name in ("cfg1", "cfg2", "cfg3"):
+        wl = bench.WORKLOADS[name]
+        eff = sum(bench.flops_per_pair(wl)) / sum(bench.issued_flops_per_pair(wl))
+        assert 0.70 < eff < 0.80, (name, eff)  # 60 of 64 pixel slots, 84 of 96 tap slots, partly empty last tile
+    # cfg1 (4 layers): ONE stem MMA per kernel row; cfg3: passes of 12 + 12 + 8 layers (3 + 3 + 2 MMAs per kernel row)
+    assert bench.issued_flops_per_pair(bench.WORKLOADS["cfg1"])[1] == 13 * 38 * 7 * 2.0 * 128 * 128 * 16
+    assert bench.issued_flops_per_pair(bench.WORKLOADS["cfg3"])[1] == 7 * 19 * 7 * 8 * 2.0 * 128 * 128 * 16
+
+
 def test_b200_arm_refuses_to_run_without_cuda():
     import torch
 
